@@ -1,0 +1,437 @@
+"""GPU bring-up probe for the tcgen05 conv / wgrad kernels (run under gpurun; not a pytest file).
+
+usage: python tools/gpu_probe.py <group>     groups: gemm conv conv2 wgrad elem
+Each case prints one line: PASS/FAIL name max_abs_err rel_err; failures dump an error map.
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vqgan-training_b200"))
+
+import torch
+import torch.nn.functional as F
+
+import native
+import plans
+from native import EPI_BIAS, EPI_MASK, EPI_RELU, EPI_RES
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+dev = "cuda"
+L = native.load()
+
+
+def report(name, got, ref, tol=2e-2):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    mx = err.max().item()
+    rel = mx / denom
+    rel2 = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+    ok = rel2 < tol and torch.isfinite(got).all().item()
+    print(f"{'PASS' if ok else 'FAIL'} {name}: max_abs={mx:.4e} ref_max={denom:.3e} rel_l2={rel2:.3e}", flush=True)
+    if not ok:
+        e2 = err.reshape(-1, err.shape[-1])
+        rows = e2.max(dim=1).values
+        cols = e2.max(dim=0).values
+        nr = min(rows.numel(), 128)
+        print("  row-err(first %d, by 8):" % nr, [f"{rows[i:i+8].max().item():.2e}" for i in range(0, nr, 8)])
+        nc = min(cols.numel(), 256)
+        print("  col-err(by 16):", [f"{cols[i:i+16].max().item():.2e}" for i in range(0, nc, 16)])
+        print("  got[0,:8]", got.reshape(-1, got.shape[-1])[0, :8].tolist())
+        print("  ref[0,:8]", ref.reshape(-1, ref.shape[-1])[0, :8].tolist())
+    return ok
+
+
+def pack_torch(w, tapmap, transpose, Kpad):
+    """w: [Cout,Cin,KH,KW] fp32 -> bf16 [R][slots][Kpad]"""
+    Cout, Cin = w.shape[:2]
+    wt = w.reshape(Cout, Cin, -1)[:, :, tapmap]  # [Cout,Cin,slots]
+    if transpose:
+        m = wt.permute(1, 2, 0)  # [Cin, slots, Cout]
+    else:
+        m = wt.permute(0, 2, 1)  # [Cout, slots, Cin]
+    out = torch.zeros(m.shape[0], m.shape[1], Kpad, device=w.device, dtype=torch.bfloat16)
+    out[:, :, : m.shape[2]] = m.to(torch.bfloat16)
+    return out.contiguous()
+
+
+def run_conv(g, x, wp, Cout, bias=None, res=None, mask=None, relu=False, out=None, out_strides=None, out_f32=False):
+    flags = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+    if res is not None:
+        flags |= EPI_RES
+    if mask is not None:
+        flags |= EPI_MASK
+    if relu:
+        flags |= EPI_RELU
+    Cs = plans.cpad(Cout)
+    if out is None:
+        out = torch.zeros(g.N, g.Ho, g.Wo, Cs, device=dev, dtype=torch.bfloat16)
+        out_strides = plans.nhwc_strides(g.Ho, g.Wo, Cs)
+    d = plans.conv_desc(g, Cout, out_strides, flags, out_f32)
+    rc = L.vqb_conv_gemm(d, native.ptr(x), native.ptr(wp), native.ptr(bias), native.ptr(res), native.ptr(mask),
+                         native.ptr(out), 0, native.stream_ptr())
+    native.check(rc, "conv_gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale)
+
+
+def case_gemm(M, K, Nn, seed=0):
+    torch.manual_seed(seed)
+    a = rnd(1, 1, M, K).to(torch.bfloat16)
+    w = rnd(Nn, K, 1, 1, scale=K ** -0.5)
+    g = plans.geom_s1(1, 1, M, K, 1)
+    wp = pack_torch(w, g.tapmap, False, K)
+    out = run_conv(g, a, wp, Nn)
+    ref = a.float().reshape(M, K) @ wp.float().reshape(Nn, K).t()
+    return report(f"gemm M={M} K={K} N={Nn}", out.reshape(M, -1)[:, :Nn], ref)
+
+
+def case_conv(N, H, W, Cin, Cout, k, seed=0, bias=False, res=False, relu=False, mask=False, nchw_f32=False):
+    torch.manual_seed(seed)
+    Cp = plans.cpad(Cin)
+    x = torch.zeros(N, H, W, Cp, device=dev, dtype=torch.bfloat16)
+    x[..., :Cin] = rnd(N, H, W, Cin).to(torch.bfloat16)
+    w = rnd(Cout, Cin, k, k, scale=(Cin * k * k) ** -0.5)
+    g = plans.geom_s1(N, H, W, Cp, k)
+    wp = pack_torch(w, g.tapmap, False, Cp)
+    b = rnd(Cout) if bias else None
+    Cs = plans.cpad(Cout)
+    r = rnd(N, H, W, Cs).to(torch.bfloat16) if res else None
+    mk = rnd(N, H, W, Cs).to(torch.bfloat16) if mask else None
+    ref = F.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2), wp.float().reshape(Cout, k * k, Cp)[:, :, :Cin]
+                   .permute(0, 2, 1).reshape(Cout, Cin, k, k), b, padding=(k - 1) // 2)
+    if res:
+        ref = ref + r[..., :Cout].float().permute(0, 3, 1, 2)
+    if relu:
+        ref = ref.relu()
+    if mask:
+        ref = ref * (mk[..., :Cout].float().permute(0, 3, 1, 2) > 0)
+    if nchw_f32:
+        out = torch.zeros(N, Cout, H, W, device=dev, dtype=torch.float32)
+        run_conv(g, x, wp, Cout, b, r, mk, relu, out=out, out_strides=plans.nchw_strides(Cout, H, W), out_f32=True)
+        got = out
+    else:
+        out = run_conv(g, x, wp, Cout, b, r, mk, relu)
+        got = out[..., :Cout].permute(0, 3, 1, 2)
+    tag = f"conv{k}x{k} N={N} {H}x{W} {Cin}->{Cout}" + (" +bias" if bias else "") + (" +res" if res else "") + \
+        (" +relu" if relu else "") + (" +mask" if mask else "") + (" nchw_f32" if nchw_f32 else "")
+    return report(tag, got.permute(0, 2, 3, 1), ref.permute(0, 2, 3, 1))
+
+
+def case_conv_s2(N, H, W, C, Cout, seed=0):
+    torch.manual_seed(seed)
+    x = rnd(N, H, W, C).to(torch.bfloat16)
+    w = rnd(Cout, C, 3, 3, scale=(C * 9) ** -0.5)
+    g = plans.geom_s2(N, H, W, C)
+    wp = pack_torch(w, g.tapmap, False, C)
+    out = run_conv(g, x, wp, Cout)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xp, w.to(torch.bfloat16).float(), stride=2)
+    return report(f"conv3x3s2 N={N} {H}x{W} {C}->{Cout}", out.float(), ref.permute(0, 2, 3, 1))
+
+
+def case_dgrad_s1(N, H, W, Cin, Cout, k, seed=0):
+    """dx = conv_transpose(dy, w): run as conv over dy with transposed/rotated packed weights."""
+    torch.manual_seed(seed)
+    Cop = plans.cpad(Cout)
+    dy = torch.zeros(N, H, W, Cop, device=dev, dtype=torch.bfloat16)
+    dy[..., :Cout] = rnd(N, H, W, Cout).to(torch.bfloat16)
+    w = rnd(Cout, Cin, k, k, scale=(Cout * k * k) ** -0.5)
+    g = plans.geom_s1_dgrad(N, H, W, Cop, k)
+    wp = pack_torch(w, g.tapmap, True, Cop)
+    out = run_conv(g, dy, wp, Cin)
+    ref = F.conv_transpose2d(dy[..., :Cout].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(),
+                             padding=(k - 1) // 2)
+    return report(f"dgrad{k}x{k} N={N} {H}x{W} Cin={Cin} Cout={Cout}", out[..., :Cin].float(),
+                  ref.permute(0, 2, 3, 1))
+
+
+def case_dgrad_s2(N, H, W, C, Cout, seed=0):
+    torch.manual_seed(seed)
+    Ho, Wo = H // 2, W // 2
+    dy = rnd(N, Ho, Wo, Cout).to(torch.bfloat16)
+    w = rnd(Cout, C, 3, 3, scale=(Cout * 9) ** -0.5)
+    dx = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
+    for ph, pw, g in plans.geom_s2_dgrad_classes(N, H, W, Cout):
+        wp = pack_torch(w, g.tapmap, True, Cout)
+        sub = dx[:, ph::2, pw::2, :]
+        strides = (H * W * C, 2 * W * C, 2 * C, 1)
+        d = plans.conv_desc(g, C, strides, 0, False)
+        base = dx.data_ptr() + (ph * W + pw) * C * 2
+        rc = L.vqb_conv_gemm(d, native.ptr(dy), native.ptr(wp), 0, 0, 0, base, 0, native.stream_ptr())
+        native.check(rc, "conv_gemm dgrad s2")
+    torch.cuda.synchronize()
+    x = torch.zeros(N, C, H, W, device=dev, requires_grad=True)
+    y = F.conv2d(F.pad(x, (0, 1, 0, 1)), w.to(torch.bfloat16).float(), stride=2)
+    (ref,) = torch.autograd.grad(y, x, dy.float().permute(0, 3, 1, 2))
+    return report(f"dgrad3x3s2 N={N} {H}x{W} {C}<-{Cout}", dx.float(), ref.permute(0, 2, 3, 1))
+
+
+def case_wgrad(N, H, W, Cin, Cout, k, ksplit, stride2=False, seed=0):
+    torch.manual_seed(seed)
+    Cp, Cop = plans.cpad(Cin), plans.cpad(Cout)
+    x = torch.zeros(N, H, W, Cp, device=dev, dtype=torch.bfloat16)
+    x[..., :Cin] = rnd(N, H, W, Cin).to(torch.bfloat16)
+    g = plans.geom_s2(N, H, W, Cp) if stride2 else plans.geom_s1(N, H, W, Cp, k)
+    dy = torch.zeros(N, g.Ho, g.Wo, Cop, device=dev, dtype=torch.bfloat16)
+    dy[..., :Cout] = rnd(N, g.Ho, g.Wo, Cout).to(torch.bfloat16)
+    d = plans.wgrad_desc(g, Cop, ksplit)
+    cols = L.vqb_wgrad_cols(len(g.taps), Cp)
+    partial = torch.full((ksplit, Cop, cols), float("nan"), device=dev, dtype=torch.float32)
+    rc = L.vqb_wgrad_gemm(d, native.ptr(dy), native.ptr(x), native.ptr(partial), native.stream_ptr())
+    native.check(rc, "wgrad_gemm")
+    T = k * k
+    grad = torch.zeros(Cout, Cin, k, k, device=dev, dtype=torch.float32)
+    tapmap = torch.tensor(g.tapmap, device=dev, dtype=torch.int32)
+    rc = L.vqb_wgrad_reduce(native.ptr(partial), native.ptr(grad), ksplit, Cout, Cop, Cin, T, len(g.taps),
+                            cols // len(g.taps), native.ptr(tapmap), 0, native.stream_ptr())
+    native.check(rc, "wgrad_reduce")
+    torch.cuda.synchronize()
+    wref = torch.zeros(Cout, Cin, k, k, device=dev, requires_grad=True)
+    xin = x[..., :Cin].float().permute(0, 3, 1, 2)
+    if stride2:
+        y = F.conv2d(F.pad(xin, (0, 1, 0, 1)), wref, stride=2)
+    else:
+        y = F.conv2d(xin, wref, padding=(k - 1) // 2)
+    (ref,) = torch.autograd.grad(y, wref, dy[..., :Cout].float().permute(0, 3, 1, 2))
+    C64 = cols // len(g.taps)
+    got_p = partial.sum(0)[:Cout].reshape(Cout, len(g.taps), C64)[:, :, :Cin]  # [Cout, slot, Cin]
+    ref_p = ref.reshape(Cout, Cin, T).permute(0, 2, 1)
+    ok = report(f"wgrad{k}x{k}{'s2' if stride2 else ''} N={N} {H}x{W} {Cin}->{Cout} ksplit={ksplit} (partial)",
+                got_p.reshape(Cout, -1), ref_p.reshape(Cout, -1), tol=1e-2)
+    if rc == 0:
+        ok &= report("   + reduce->OIHW", grad.reshape(Cout, -1), ref.reshape(Cout, -1), tol=1e-2)
+    return ok
+
+
+def bench_conv(N, H, W, Cin, Cout, k, iters=20):
+    torch.manual_seed(0)
+    x = rnd(N, H, W, Cin).to(torch.bfloat16)
+    w = rnd(Cout, Cin, k, k, scale=(Cin * k * k) ** -0.5)
+    g = plans.geom_s1(N, H, W, Cin, k)
+    wp = pack_torch(w, g.tapmap, False, Cin)
+    out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    d = plans.conv_desc(g, Cout, plans.nhwc_strides(H, W, Cout), 0, False)
+    args = (d, native.ptr(x), native.ptr(wp), 0, 0, 0, native.ptr(out), 0, native.stream_ptr())
+    for _ in range(3):
+        native.check(L.vqb_conv_gemm(*args))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        L.vqb_conv_gemm(*args)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 2.0 * N * H * W * Cout * Cin * k * k
+    # cudnn bf16 reference timing
+    xc = x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+    wc = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
+        F.conv2d(xc, wc, padding=(k - 1) // 2)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        F.conv2d(xc, wc, padding=(k - 1) // 2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_ref = e0.elapsed_time(e1) / iters
+    print(f"BENCH conv{k}x{k} N={N} {H}x{W} {Cin}->{Cout}: ours {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s | "
+          f"cudnn bf16 {ms_ref:.3f} ms = {fl / ms_ref / 1e9:.1f} TFLOP/s", flush=True)
+
+
+def bench_wgrad(N, H, W, Cin, Cout, k, ksplit, iters=10):
+    torch.manual_seed(0)
+    x = rnd(N, H, W, Cin).to(torch.bfloat16)
+    dy = rnd(N, H, W, Cout).to(torch.bfloat16)
+    g = plans.geom_s1(N, H, W, Cin, k)
+    d = plans.wgrad_desc(g, Cout, ksplit)
+    cols = L.vqb_wgrad_cols(len(g.taps), Cin)
+    partial = torch.zeros(ksplit, Cout, cols, device=dev, dtype=torch.float32)
+    args = (d, native.ptr(dy), native.ptr(x), native.ptr(partial), native.stream_ptr())
+    for _ in range(2):
+        native.check(L.vqb_wgrad_gemm(*args))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        L.vqb_wgrad_gemm(*args)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 2.0 * N * H * W * Cout * Cin * k * k
+    print(f"BENCH wgrad{k}x{k} N={N} {H}x{W} {Cin}->{Cout} ksplit={ksplit}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s",
+          flush=True)
+
+
+def group_elem():
+    ok = True
+    torch.manual_seed(0)
+    # pack_weights vs torch
+    for (Cout, Cin, k, tr) in [(64, 48, 3, 0), (64, 48, 3, 1), (5, 128, 1, 0), (128, 3, 3, 1)]:
+        w = rnd(Cout, Cin, k, k)
+        tapmap = list(range(k * k))[::-1] if tr else list(range(k * k))
+        Kpad = plans.cpad(Cout if tr else Cin)
+        R = Cin if tr else Cout
+        out = torch.zeros(R, k * k, Kpad, device=dev, dtype=torch.bfloat16)
+        tm = torch.tensor(tapmap, device=dev, dtype=torch.int32)
+        native.check(L.vqb_pack_weights(native.ptr(w), native.ptr(out), Cout, Cin, k * k, k * k, native.ptr(tm), tr,
+                                        Kpad, native.stream_ptr()))
+        torch.cuda.synchronize()
+        ok &= report(f"pack_weights {Cout}x{Cin}x{k} tr={tr}", out.reshape(R, -1), pack_torch(w, tapmap, bool(tr), Kpad).reshape(R, -1), tol=1e-6)
+    # layout conversion
+    x = rnd(2, 3, 24, 40)
+    shift = torch.tensor([-0.03, -0.088, -0.188], device=dev)
+    iscale = 1.0 / torch.tensor([0.458, 0.448, 0.45], device=dev)
+    y = torch.full((2, 24, 40, 8), 7.0, device=dev, dtype=torch.bfloat16)
+    native.check(L.vqb_nchw_to_nhwc(native.ptr(x), native.ptr(y), 2, 3, 24, 40, 8, native.ptr(shift), native.ptr(iscale), native.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.zeros(2, 24, 40, 8, device=dev)
+    ref[..., :3] = ((x - shift[None, :, None, None]) * iscale[None, :, None, None]).permute(0, 2, 3, 1)
+    ok &= report("nchw_to_nhwc scaled", y, ref, tol=1e-2)
+    gx = torch.zeros(2, 3, 24, 40, device=dev)
+    native.check(L.vqb_nhwc_to_nchw(native.ptr(y), native.ptr(gx), 2, 3, 24, 40, 8, native.ptr(iscale), native.stream_ptr()))
+    torch.cuda.synchronize()
+    ok &= report("nhwc_to_nchw scaled", gx.permute(0, 2, 3, 1), y[..., :3].float() * iscale, tol=1e-6)
+    # GroupNorm + SiLU fwd/bwd
+    for (N, H, W, Cc, silu) in [(2, 16, 16, 128, 1), (3, 8, 8, 32, 1), (1, 64, 64, 256, 0), (2, 32, 32, 512, 1), (2, 10, 6, 64, 1)]:
+        xx = (rnd(N, H, W, Cc) * 2 + 0.5).to(torch.bfloat16)
+        gamma = rnd(Cc) * 0.5 + 1
+        beta = rnd(Cc) * 0.2
+        yy = torch.zeros_like(xx)
+        mr = torch.zeros(N, 32, 2, device=dev)
+        ws = torch.zeros(N * Cc * 2, device=dev, dtype=torch.float64)
+        native.check(L.vqb_gn_silu_fwd(native.ptr(xx), native.ptr(yy), native.ptr(gamma), native.ptr(beta), native.ptr(mr),
+                                       native.ptr(ws), N, H * W, Cc, 32, 1e-6, silu, native.stream_ptr()))
+        torch.cuda.synchronize()
+        xr = xx.float().permute(0, 3, 1, 2).requires_grad_(True)
+        gr = gamma.clone().requires_grad_(True)
+        br = beta.clone().requires_grad_(True)
+        yr = F.group_norm(xr, 32, gr, br, 1e-6)
+        if silu:
+            yr = yr * torch.sigmoid(yr)
+        ok &= report(f"gn_silu_fwd N={N} {H}x{W} C={Cc} silu={silu}", yy, yr.permute(0, 2, 3, 1), tol=1e-2)
+        dy = rnd(N, H, W, Cc).to(torch.bfloat16)
+        addt = rnd(N, H, W, Cc).to(torch.bfloat16)
+        dx = torch.zeros_like(xx)
+        dg = torch.zeros(Cc, device=dev)
+        db = torch.zeros(Cc, device=dev)
+        ws2 = torch.zeros(N * Cc * 2 + N * 32 * 2, device=dev)
+        native.check(L.vqb_gn_silu_bwd(native.ptr(xx), native.ptr(dy), native.ptr(addt), native.ptr(dx), native.ptr(gamma),
+                                       native.ptr(beta), native.ptr(mr), native.ptr(dg), native.ptr(db), native.ptr(ws2),
+                                       N, H * W, Cc, 32, silu, native.stream_ptr()))
+        torch.cuda.synchronize()
+        gxr, ggr, gbr = torch.autograd.grad(yr, (xr, gr, br), dy.float().permute(0, 3, 1, 2))
+        ok &= report("   bwd dx(+add)", dx, gxr.permute(0, 2, 3, 1) + addt.float(), tol=1e-2)
+        ok &= report("   bwd dgamma", dg[None], ggr[None], tol=1e-2)
+        ok &= report("   bwd dbeta", db[None], gbr[None], tol=1e-2)
+    # upsample
+    xu = rnd(2, 8, 12, 64).to(torch.bfloat16)
+    yu = torch.zeros(2, 16, 24, 64, device=dev, dtype=torch.bfloat16)
+    native.check(L.vqb_upsample2x_fwd(native.ptr(xu), native.ptr(yu), 2, 8, 12, 64, native.stream_ptr()))
+    ref = F.interpolate(xu.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    ok &= report("upsample2x fwd", yu, ref, tol=1e-6)
+    dyu = rnd(2, 16, 24, 64).to(torch.bfloat16)
+    dxu = torch.zeros_like(xu)
+    native.check(L.vqb_upsample2x_bwd(native.ptr(dyu), native.ptr(dxu), 2, 8, 12, 64, native.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = F.avg_pool2d(dyu.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1) * 4
+    ok &= report("upsample2x bwd", dxu, ref, tol=1e-2)
+    # colsum
+    xc = rnd(5000, 128).to(torch.bfloat16)
+    oc = torch.zeros(128, device=dev)
+    native.check(L.vqb_colsum(native.ptr(xc), native.ptr(oc), 5000, 128, native.stream_ptr()))
+    torch.cuda.synchronize()
+    ok &= report("colsum", oc[None], xc.float().sum(0)[None], tol=1e-3)
+    return ok
+
+
+def group_gemm():
+    ok = True
+    ok &= case_gemm(128, 64, 16)
+    ok &= case_gemm(128, 64, 64)
+    ok &= case_gemm(256, 128, 128)
+    ok &= case_gemm(1024, 512, 256)
+    ok &= case_gemm(4096, 256, 512)
+    ok &= case_gemm(200, 64, 40)
+    return ok
+
+
+def group_conv():
+    ok = True
+    ok &= case_conv(2, 16, 16, 64, 64, 1)
+    ok &= case_conv(2, 16, 16, 64, 64, 3)
+    ok &= case_conv(2, 32, 32, 128, 128, 3, bias=True)
+    ok &= case_conv(2, 32, 32, 512, 512, 3, bias=True, res=True)
+    ok &= case_conv(1, 256, 256, 128, 128, 3)
+    ok &= case_conv(4, 8, 8, 64, 128, 3, relu=True, bias=True)
+    ok &= case_conv(3, 4, 4, 64, 64, 3)
+    ok &= case_conv(2, 20, 20, 64, 64, 3, bias=True)
+    ok &= case_conv(1, 24, 40, 128, 64, 3)
+    return ok
+
+
+def group_conv2():
+    ok = True
+    ok &= case_conv(2, 32, 32, 16, 512, 3, bias=True)
+    ok &= case_conv(2, 32, 32, 32, 64, 3)
+    ok &= case_conv(2, 32, 32, 3, 128, 3, bias=True)
+    ok &= case_conv(2, 32, 32, 512, 16, 3, bias=True, nchw_f32=True)
+    ok &= case_conv(2, 64, 64, 128, 3, 3, bias=True, nchw_f32=True)
+    ok &= case_conv(2, 32, 32, 128, 128, 3, mask=True)
+    ok &= case_conv(2, 32, 32, 128, 3, 3)
+    ok &= case_conv_s2(2, 32, 32, 128, 128)
+    ok &= case_conv_s2(1, 64, 64, 256, 256)
+    ok &= case_dgrad_s1(2, 32, 32, 128, 256, 3)
+    ok &= case_dgrad_s1(2, 16, 16, 64, 64, 1)
+    ok &= case_dgrad_s1(2, 32, 32, 3, 64, 3)
+    ok &= case_dgrad_s2(2, 32, 32, 128, 128)
+    return ok
+
+
+def group_wgrad():
+    ok = True
+    ok &= case_wgrad(2, 16, 16, 64, 64, 1, 1)
+    ok &= case_wgrad(2, 16, 16, 64, 64, 3, 1)
+    ok &= case_wgrad(2, 32, 32, 128, 128, 3, 4)
+    ok &= case_wgrad(2, 32, 32, 128, 256, 3, 2)
+    ok &= case_wgrad(2, 16, 16, 512, 512, 3, 3)
+    ok &= case_wgrad(1, 64, 64, 256, 128, 1, 8)
+    ok &= case_wgrad(2, 20, 20, 64, 64, 3, 2)
+    ok &= case_wgrad(4, 4, 4, 64, 64, 3, 1)
+    ok &= case_wgrad(2, 32, 32, 16, 512, 3, 2)
+    ok &= case_wgrad(2, 32, 32, 128, 128, 3, 2, stride2=True)
+    return ok
+
+
+def group_bench():
+    bench_conv(8, 64, 64, 512, 512, 3)
+    bench_conv(8, 256, 256, 128, 128, 3)
+    bench_conv(8, 128, 128, 256, 256, 3)
+    bench_conv(8, 32, 32, 512, 512, 3)
+    bench_conv(8, 128, 128, 512, 256, 1)
+    bench_wgrad(8, 64, 64, 512, 512, 3, 4)
+    bench_wgrad(8, 256, 256, 128, 128, 3, 32)
+    bench_wgrad(8, 128, 128, 256, 256, 3, 8)
+    return True
+
+
+if __name__ == "__main__":
+    grp = sys.argv[1]
+    t0 = time.time()
+    print(f"== group {grp}: device_ok={L.vqb_device_ok()} {torch.cuda.get_device_name(0)}", flush=True)
+    ok = globals()["group_" + grp]()
+    print(f"== group {grp} {'ALL PASS' if ok else 'HAS FAILURES'} in {time.time() - t0:.1f}s launches={native.launch_count()}",
+          flush=True)
+    sys.exit(0 if ok else 1)

@@ -1,0 +1,381 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (forward and data-gradient).
+//
+//   out[n,h,w,co] = epi( sum_t sum_c A_view(t)[n, h+dh_t, w+dw_t, c] * Wp[co][t*C + c] )
+//
+// GEMM view: M = output pixels (tiles of 128 = BW x BH x BN box of the NHWC tensor), N = Cout,
+// K = ntaps * C walked in 64-channel chunks. Per K-chunk the TMA producer issues ONE 4-D tiled load
+// of the activation box shifted by the tap offset (out-of-range rows/cols/channels are zero-filled by
+// the TMA unit -> conv padding costs nothing) and ONE 2-D load of the packed weights; both land in
+// 128B-swizzled K-major smem tiles that a single thread feeds to tcgen05.mma (M=128, N=BLOCK_N,
+// K=16 x4). Accumulators live in TMEM, double buffered, so the 4 epilogue warps drain tile i
+// (tcgen05.ld -> bias/residual/ReLU/mask -> bf16 NHWC or strided fp32) while tile i+1 is in the MMA
+// pipe. Persistent: one CTA per SM walks tiles round-robin.
+//
+// Replaces the cuDNN kernels behind nn.Conv2d at reference ae.py:105-117,143-154,160-167 and the
+// torchvision VGG convs reached from utils.py:95-111,150-154 (see include/vqb200.h).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vqb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per stage
+constexpr int kThreads = 256;                   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kMaxStages = 8;
+
+struct alignas(64) ConvParams {
+    CUtensorMap amap[VQB_MAX_VIEWS];
+    CUtensorMap bmap;
+    int32_t tap_view[VQB_MAX_TAPS];
+    int32_t tap_dw[VQB_MAX_TAPS];
+    int32_t tap_dh[VQB_MAX_TAPS];
+    int32_t ntaps, kchunks, C, Cout;
+    int32_t N, H, W;
+    int32_t lbw, lbh, lbn;
+    int32_t tiles_w, tiles_h, tiles_nb;
+    int32_t n_tiles, total_tiles;
+    int32_t block_n, stages, tmem_cols;
+    int32_t flags, out_f32;
+    int64_t on, oh, ow, oc;
+    void* out;
+    const void* res;
+    const void* mask;
+    const float* bias;
+    float* stats;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+
+    // carve shared memory (1024-B aligned for the 128B swizzle atoms)
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t stages = p.stages;
+    const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
+    uint8_t* sA = base;
+    uint8_t* sB = base + stages * kABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_bytes);
+    uint64_t* empty = full + stages;
+    uint64_t* tfull = empty + stages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    if (warp == 0 && lane == 0) {
+        for (int v = 0; v < VQB_MAX_VIEWS; ++v) {
+            bool used = false;
+            for (int t = 0; t < p.ntaps; ++t) used |= (p.tap_view[t] == v);
+            if (used) tma_prefetch_desc(&p.amap[v]);
+        }
+        tma_prefetch_desc(&p.bmap);
+    }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t i = 0; i < stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_kb = p.ntaps * p.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            const int m_tile = tile / p.n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            const int th = (m_tile / p.tiles_w) % p.tiles_h;
+            const int tn = m_tile / (p.tiles_w * p.tiles_h);
+            const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
+            for (int t = 0; t < p.ntaps; ++t) {
+                const CUtensorMap* am = &p.amap[p.tap_view[t]];
+                const int cw = w0 + p.tap_dw[t], chh = h0 + p.tap_dh[t];
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
+                    tma_load_4d(am, &full[stage], sA + stage * kABytes, kc * kBlockK, cw, chh, n0);
+                    tma_load_2d(&p.bmap, &full[stage], sB + stage * b_bytes, t * p.C + kc * kBlockK,
+                                n_tile * p.block_n);
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer (single thread) =====================
+        const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+        uint32_t stage = 0, phase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(&tempty[as], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * p.block_n;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+                const uint32_t b_addr = smem_u32(sB + stage * b_bytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, 2);
+                    const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, 2);
+                    umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (4 warps = 128 accumulator rows) =====================
+        const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        const uint32_t row = ew * 32 + lane;
+        const int wi = row & ((1 << p.lbw) - 1);
+        const int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
+        const int ni = row >> (p.lbw + p.lbh);
+        const bool has_bias = p.flags & VQB_EPI_BIAS, has_res = p.flags & VQB_EPI_RES;
+        const bool do_relu = p.flags & VQB_EPI_RELU, has_mask = p.flags & VQB_EPI_MASK;
+        const bool vec_path = (p.oc == 1) && (p.out_f32 == 0);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            const int n_tile = tile % p.n_tiles;
+            const int m_tile = tile / p.n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            const int th = (m_tile / p.tiles_w) % p.tiles_h;
+            const int tn = m_tile / (p.tiles_w * p.tiles_h);
+            const int w = (tw << p.lbw) + wi, h = (th << p.lbh) + hi, n = (tn << p.lbn) + ni;
+            const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+            const int64_t pix = static_cast<int64_t>(n) * p.on + static_cast<int64_t>(h) * p.oh +
+                                static_cast<int64_t>(w) * p.ow;
+            const int col0 = n_tile * p.block_n;
+
+            mbar_wait(&tfull[as], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + as * p.block_n;
+            for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                const int col = col0 + c0;
+                if (col >= p.Cout) continue;  // warp-uniform
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (has_bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < p.Cout) f[j] += __ldg(p.bias + col + j);
+                }
+                const bool full16 = (col + 16 <= p.Cout);
+                if (vec_path && full16) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix + col;
+                    if (valid) {
+                        if (has_res) {
+                            const uint4* r = reinterpret_cast<const uint4*>(
+                                reinterpret_cast<const __nv_bfloat16*>(p.res) + pix + col);
+                            uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float2 t = unpack_bf16x2(rr[j]);
+                                f[2 * j] += t.x;
+                                f[2 * j + 1] += t.y;
+                            }
+                        }
+                        if (do_relu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        if (has_mask) {
+                            const uint4* m = reinterpret_cast<const uint4*>(
+                                reinterpret_cast<const __nv_bfloat16*>(p.mask) + pix + col);
+                            uint4 m0 = __ldg(m), m1 = __ldg(m + 1);
+                            const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float2 t = unpack_bf16x2(mm[j]);
+                                if (!(t.x > 0.f)) f[2 * j] = 0.f;
+                                if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
+                            }
+                        }
+                        uint4 o0, o1;
+                        o0.x = pack_bf16x2(f[0], f[1]);
+                        o0.y = pack_bf16x2(f[2], f[3]);
+                        o0.z = pack_bf16x2(f[4], f[5]);
+                        o0.w = pack_bf16x2(f[6], f[7]);
+                        o1.x = pack_bf16x2(f[8], f[9]);
+                        o1.y = pack_bf16x2(f[10], f[11]);
+                        o1.z = pack_bf16x2(f[12], f[13]);
+                        o1.w = pack_bf16x2(f[14], f[15]);
+                        reinterpret_cast<uint4*>(o)[0] = o0;
+                        reinterpret_cast<uint4*>(o)[1] = o1;
+                    }
+                } else if (valid) {
+                    // generic strided / ragged path (small Cout, NCHW fp32 outputs)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (col + j < p.Cout) {
+                            const int64_t a = pix + static_cast<int64_t>(col + j) * p.oc;
+                            float x = f[j];
+                            if (has_res) x += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[a]);
+                            if (do_relu) x = fmaxf(x, 0.f);
+                            if (has_mask &&
+                                !(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mask)[a]) > 0.f))
+                                x = 0.f;
+                            if (p.out_f32)
+                                reinterpret_cast<float*>(p.out)[a] = x;
+                            else
+                                reinterpret_cast<__nv_bfloat16*>(p.out)[a] = __float2bfloat16(x);
+                            f[j] = x;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+static int fill_views(const VqbView* views, int nviews, const void* a, int C, int lbw, int lbh, int lbn,
+                      CUtensorMap* maps) {
+    for (int v = 0; v < nviews; ++v) {
+        const VqbView& vw = views[v];
+        uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(vw.Wv), static_cast<uint64_t>(vw.Hv),
+                            static_cast<uint64_t>(vw.Nv)};
+        uint64_t str[3] = {static_cast<uint64_t>(vw.sw) * 2, static_cast<uint64_t>(vw.sh) * 2,
+                           static_cast<uint64_t>(vw.sn) * 2};
+        uint32_t box[4] = {kBlockK, 1u << lbw, 1u << lbh, 1u << lbn};
+        const void* base = static_cast<const uint8_t*>(a) + vw.offset * 2;
+        int rc = encode_tmap_bf16(&maps[v], base, 4, dims, str, box, 128);
+        if (rc != VQB_OK) return rc;
+    }
+    return VQB_OK;
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias,
+                             const void* res, const void* mask, void* out, float* stats, void* stream) {
+    VQB_CHECK(d && a && w_packed && out, "vqb_conv_gemm: null pointer");
+    VQB_CHECK(d->C > 0 && d->C % 8 == 0, "vqb_conv_gemm: C=%d must be a positive multiple of 8", d->C);
+    VQB_CHECK(d->Cout > 0 && d->N > 0 && d->H > 0 && d->W > 0, "vqb_conv_gemm: bad extents");
+    VQB_CHECK(d->ntaps >= 1 && d->ntaps <= VQB_MAX_TAPS && d->nviews >= 1 && d->nviews <= VQB_MAX_VIEWS,
+              "vqb_conv_gemm: ntaps=%d nviews=%d out of range", d->ntaps, d->nviews);
+    VQB_CHECK(((int64_t)d->ntaps * d->C) % 8 == 0, "vqb_conv_gemm: weight row stride must be 16-byte aligned");
+    if ((d->flags & VQB_EPI_BIAS)) VQB_CHECK(bias != nullptr, "vqb_conv_gemm: VQB_EPI_BIAS without bias");
+    if ((d->flags & VQB_EPI_RES)) VQB_CHECK(res != nullptr, "vqb_conv_gemm: VQB_EPI_RES without res");
+    if ((d->flags & VQB_EPI_MASK)) VQB_CHECK(mask != nullptr, "vqb_conv_gemm: VQB_EPI_MASK without mask");
+    VQB_CHECK(!(d->flags & VQB_EPI_STATS), "vqb_conv_gemm: VQB_EPI_STATS not implemented yet");
+    if (d->oc == 1 && !d->out_f32) {
+        VQB_CHECK(d->on % 8 == 0 && d->oh % 8 == 0 && d->ow % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+                  "vqb_conv_gemm: NHWC bf16 output needs 16-byte aligned pixel rows");
+    }
+    for (int t = 0; t < d->ntaps; ++t)
+        VQB_CHECK(d->taps[t].view >= 0 && d->taps[t].view < d->nviews, "vqb_conv_gemm: tap %d view out of range", t);
+    if (!device_is_sm100()) return set_error(VQB_ENODEVICE, "vqb_conv_gemm: current device is not sm_100");
+
+    ConvParams p;  // ~2.5 KB, filled per call, passed by value (__grid_constant__) to the kernel
+    // box of 128 output pixels
+    uint32_t bw = next_pow2(d->W);
+    if (bw > 128) bw = 128;
+    uint32_t bh = next_pow2(d->H);
+    if (bh > 128 / bw) bh = 128 / bw;
+    uint32_t bn = 128 / (bw * bh);
+    p.lbw = ilog2(bw);
+    p.lbh = ilog2(bh);
+    p.lbn = ilog2(bn);
+    p.tiles_w = (d->W + bw - 1) / bw;
+    p.tiles_h = (d->H + bh - 1) / bh;
+    p.tiles_nb = (d->N + bn - 1) / bn;
+    int block_n;
+    if (d->Cout >= 256)
+        block_n = 256;
+    else
+        block_n = ((d->Cout + 15) / 16) * 16;
+    p.block_n = block_n;
+    p.n_tiles = (d->Cout + block_n - 1) / block_n;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
+    const int stage_bytes = kABytes + block_n * kBlockK * 2;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    p.stages = stages;
+    uint32_t tc = next_pow2(2 * block_n);
+    if (tc < 32) tc = 32;
+    p.tmem_cols = tc;
+    p.ntaps = d->ntaps;
+    p.kchunks = (d->C + kBlockK - 1) / kBlockK;
+    p.C = d->C;
+    p.Cout = d->Cout;
+    p.N = d->N;
+    p.H = d->H;
+    p.W = d->W;
+    p.flags = d->flags;
+    p.out_f32 = d->out_f32;
+    p.on = d->on;
+    p.oh = d->oh;
+    p.ow = d->ow;
+    p.oc = d->oc;
+    p.out = out;
+    p.res = res;
+    p.mask = mask;
+    p.bias = bias;
+    p.stats = stats;
+    for (int t = 0; t < d->ntaps; ++t) {
+        p.tap_view[t] = d->taps[t].view;
+        p.tap_dw[t] = d->taps[t].dw;
+        p.tap_dh[t] = d->taps[t].dh;
+    }
+    int rc = fill_views(d->views, d->nviews, a, d->C, p.lbw, p.lbh, p.lbn, p.amap);
+    if (rc != VQB_OK) return rc;
+    {
+        const uint64_t ktot = static_cast<uint64_t>(d->ntaps) * d->C;
+        uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->Cout)};
+        uint64_t str[1] = {ktot * 2};
+        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+        rc = encode_tmap_bf16(&p.bmap, w_packed, 2, dims, str, box, 128);
+        if (rc != VQB_OK) return rc;
+    }
+    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_gemm_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}

@@ -1,0 +1,576 @@
+// HBM-bound kernels of the VAE path: layout conversion at the module boundary, weight packing,
+// fused GroupNorm(+SiLU) forward / backward, nearest-2x up-sampling, bias gradients, wgrad split
+// reduction. All activations are NHWC bf16 with C % 8 == 0; every thread moves 16-byte vectors and
+// owns a FIXED 8-channel slot (its channel vector index never changes while it strides over pixels),
+// so per-channel affine terms / reductions stay in registers.
+//
+// Reference semantics: FP32GroupNorm ae.py:41-53 (32 groups, biased variance, eps inside sqrt,
+// fp32 math), swish ae.py:13-14, Upsample ae.py:157-167 (nearest), Conv2d bias gradients.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vqb {
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]);
+    u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]);
+    u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------ weight packing
+// out[r][slot][k] (bf16), r < R, k < Kpad:  transpose ? w[k][r][tap] : w[r][k][tap]   (w is OIHW fp32,
+// tap = tapmap[slot] indexes KH*KW), zero for k >= K.
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                    int T, int nslots, const int* __restrict__ tapmap, int transpose, int Kpad,
+                                    int fold /* 0 none */) {
+    const int R = transpose ? Cin : Cout;
+    const int K = transpose ? Cout : Cin;
+    const int64_t total = static_cast<int64_t>(R) * nslots * Kpad;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % Kpad);
+        const int slot = static_cast<int>((i / Kpad) % nslots);
+        const int r = static_cast<int>(i / (static_cast<int64_t>(Kpad) * nslots));
+        float v = 0.f;
+        if (k < K) {
+            const int tap = tapmap[slot];
+            const int co = transpose ? k : r, ci = transpose ? r : k;
+            v = w[(static_cast<int64_t>(co) * Cin + ci) * T + tap];
+        }
+        out[i] = __float2bfloat16(v);
+    }
+}
+
+// ------------------------------------------------------------------ layout conversion
+// y[n,h,w,c] = (x[n,c,h,w] - shift[c]) * inv_scale[c]   (bf16 NHWC, channels >= C zero)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int HW,
+                                    int Cpad, const float* __restrict__ shift, const float* __restrict__ inv_scale) {
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t n = i / HW, p = i % HW;
+        const float* xp = x + n * C * HW + p;
+        __nv_bfloat16* yp = y + i * Cpad;
+        for (int c0 = 0; c0 < Cpad; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                float v = 0.f;
+                if (c < C) {
+                    v = xp[static_cast<int64_t>(c) * HW];
+                    if (shift) v = (v - shift[c]) * inv_scale[c];
+                }
+                f[j] = v;
+            }
+            store8(yp + c0, f);
+        }
+    }
+}
+
+// gx[n,c,h,w] = g[n,h,w,c] * inv_scale[c]   (fp32 NCHW out)
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ gx, int N, int C, int HW,
+                                    int Cpad, const float* __restrict__ inv_scale) {
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t n = i / HW, p = i % HW;
+        const __nv_bfloat16* gp = g + i * Cpad;
+        float* xp = gx + n * C * HW + p;
+        for (int c = 0; c < C; ++c) {
+            float v = __bfloat162float(gp[c]);
+            if (inv_scale) v *= inv_scale[c];
+            xp[static_cast<int64_t>(c) * HW] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ GroupNorm forward
+// grid (chunks, N); thread t owns channel vector cv = t % V (V = C/8) and pixel rows t / V + k*R.
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ sums /* [N][C][2] */, int HW,
+                                int C, int pix_per_chunk) {
+    extern __shared__ float sm[];  // [C][2]
+    const int V = C >> 3, R = blockDim.x / V;
+    const int cv = threadIdx.x % V, pr = threadIdx.x / V;
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const int p0 = blockIdx.x * pix_per_chunk;
+    const int p1 = min(HW, p0 + pix_per_chunk);
+    if (pr < R) {
+        const __nv_bfloat16* xb = x + (static_cast<int64_t>(n) * HW) * C + cv * 8;
+        for (int p = p0 + pr; p < p1; p += R) {
+            float f[8];
+            load8(xb + static_cast<int64_t>(p) * C, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += f[j];
+                q[j] += f[j] * f[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sm[(cv * 8 + j) * 2], s[j]);
+            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], q[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+        atomicAdd(&sums[static_cast<int64_t>(n) * 2 * C + i], static_cast<double>(sm[i]));
+}
+
+// mean / rstd per (n, group) from the per-channel double sums.
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __restrict__ mr /* [N][G][2] */, int N,
+                                   int C, int G, int HW, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * G) return;
+    const int n = i / G, g = i % G, cpg = C / G;
+    double s = 0, q = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        s += sums[(static_cast<int64_t>(n) * C + c) * 2];
+        q += sums[(static_cast<int64_t>(n) * C + c) * 2 + 1];
+    }
+    const double m = static_cast<double>(cpg) * HW;
+    const double mean = s / m;
+    double var = q / m - mean * mean;
+    if (var < 0) var = 0;
+    mr[i * 2] = static_cast<float>(mean);
+    mr[i * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                const float* __restrict__ mr, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int HW, int C, int G, int pix_per_chunk, int silu) {
+    const int V = C >> 3, R = blockDim.x / V;
+    const int cv = threadIdx.x % V, pr = threadIdx.x / V;
+    if (pr >= R) return;
+    const int n = blockIdx.y, cpg = C / G;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j, g = c / cpg;
+        const float mean = mr[(n * G + g) * 2], rstd = mr[(n * G + g) * 2 + 1];
+        a[j] = rstd * gamma[c];
+        b[j] = beta[c] - mean * a[j];
+    }
+    const int p0 = blockIdx.x * pix_per_chunk;
+    const int p1 = min(HW, p0 + pix_per_chunk);
+    const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+    for (int p = p0 + pr; p < p1; p += R) {
+        float f[8];
+        load8(x + base + static_cast<int64_t>(p) * C, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float u = fmaf(a[j], f[j], b[j]);
+            f[j] = silu ? u * sigmoidf_(u) : u;
+        }
+        store8(y + base + static_cast<int64_t>(p) * C, f);
+    }
+}
+
+// ------------------------------------------------------------------ GroupNorm backward
+// per-(n,channel) sums of du and du*xhat, du = dy * silu'(u), u = xhat*gamma + beta
+__global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                     const float* __restrict__ mr, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ cs /* [N][C][2] */, int HW,
+                                     int C, int G, int pix_per_chunk, int silu) {
+    extern __shared__ float sm[];  // [C][2]
+    const int V = C >> 3, R = blockDim.x / V;
+    const int cv = threadIdx.x % V, pr = threadIdx.x / V;
+    const int n = blockIdx.y, cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    if (pr < R) {
+        float mean[8], rstd[8], ga[8], be[8], s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j, g = c / cpg;
+            mean[j] = mr[(n * G + g) * 2];
+            rstd[j] = mr[(n * G + g) * 2 + 1];
+            ga[j] = gamma[c];
+            be[j] = beta[c];
+            s1[j] = s2[j] = 0.f;
+        }
+        const int p0 = blockIdx.x * pix_per_chunk;
+        const int p1 = min(HW, p0 + pix_per_chunk);
+        const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+        for (int p = p0 + pr; p < p1; p += R) {
+            float f[8], d[8];
+            load8(x + base + static_cast<int64_t>(p) * C, f);
+            load8(dy + base + static_cast<int64_t>(p) * C, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[j] - mean[j]) * rstd[j];
+                float du = d[j];
+                if (silu) {
+                    const float u = fmaf(xh, ga[j], be[j]);
+                    const float sg = sigmoidf_(u);
+                    du *= sg * (1.f + u * (1.f - sg));
+                }
+                s1[j] += du;
+                s2[j] += du * xh;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sm[(cv * 8 + j) * 2], s1[j]);
+            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], s2[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&cs[static_cast<int64_t>(n) * 2 * C + i], sm[i]);
+}
+
+// gs[n][g] = (sum_c gamma_c*s1, sum_c gamma_c*s2) / m ; dgamma[c] = sum_n s2 ; dbeta[c] = sum_n s1
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ cs, const float* __restrict__ gamma,
+                                       float* __restrict__ gs /* [N][G][2] */, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int N, int C, int G, int HW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cpg = C / G;
+    if (i < N * G) {
+        const int n = i / G, g = i % G;
+        float a = 0.f, b = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += gamma[c] * cs[(static_cast<int64_t>(n) * C + c) * 2];
+            b += gamma[c] * cs[(static_cast<int64_t>(n) * C + c) * 2 + 1];
+        }
+        const float m = static_cast<float>(cpg) * HW;
+        gs[i * 2] = a / m;
+        gs[i * 2 + 1] = b / m;
+    }
+    if (i < C) {
+        float a = 0.f, b = 0.f;
+        for (int n = 0; n < N; ++n) {
+            a += cs[(static_cast<int64_t>(n) * C + i) * 2];
+            b += cs[(static_cast<int64_t>(n) * C + i) * 2 + 1];
+        }
+        dbeta[i] = a;
+        dgamma[i] = b;
+    }
+}
+
+// dx = rstd * (du*gamma - S1 - xhat*S2) (+ add)
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
+                                    const float* __restrict__ mr, const float* __restrict__ gs,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                                    int G, int pix_per_chunk, int silu) {
+    const int V = C >> 3, R = blockDim.x / V;
+    const int cv = threadIdx.x % V, pr = threadIdx.x / V;
+    if (pr >= R) return;
+    const int n = blockIdx.y, cpg = C / G;
+    float mean[8], rstd[8], ga[8], be[8], S1[8], S2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j, g = c / cpg;
+        mean[j] = mr[(n * G + g) * 2];
+        rstd[j] = mr[(n * G + g) * 2 + 1];
+        S1[j] = gs[(n * G + g) * 2];
+        S2[j] = gs[(n * G + g) * 2 + 1];
+        ga[j] = gamma[c];
+        be[j] = beta[c];
+    }
+    const int p0 = blockIdx.x * pix_per_chunk;
+    const int p1 = min(HW, p0 + pix_per_chunk);
+    const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+    for (int p = p0 + pr; p < p1; p += R) {
+        float f[8], d[8], r[8];
+        const int64_t off = base + static_cast<int64_t>(p) * C;
+        load8(x + off, f);
+        load8(dy + off, d);
+        if (add) load8(add + off, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - mean[j]) * rstd[j];
+            float du = d[j];
+            if (silu) {
+                const float u = fmaf(xh, ga[j], be[j]);
+                const float sg = sigmoidf_(u);
+                du *= sg * (1.f + u * (1.f - sg));
+            }
+            float v = rstd[j] * (du * ga[j] - S1[j] - xh * S2[j]);
+            if (add) v += r[j];
+            f[j] = v;
+        }
+        store8(dx + off, f);
+    }
+}
+
+// ------------------------------------------------------------------ nearest 2x up-sampling
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                  int W, int C) {
+    const int V = C >> 3;
+    const int64_t total = static_cast<int64_t>(N) * H * W * V;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int cv = static_cast<int>(i % V);
+        const int64_t pix = i / V;
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const int64_t n = pix / (static_cast<int64_t>(W) * H);
+        const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + cv * 8);
+        __nv_bfloat16* o = y + ((n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * 8;
+        *reinterpret_cast<uint4*>(o) = u;
+        *reinterpret_cast<uint4*>(o + C) = u;
+        *reinterpret_cast<uint4*>(o + static_cast<int64_t>(2) * W * C) = u;
+        *reinterpret_cast<uint4*>(o + static_cast<int64_t>(2) * W * C + C) = u;
+    }
+}
+
+// dx[n,h,w,c] = sum of the 2x2 block of dy (fp32 add, one rounding)
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
+                                      int H, int W, int C) {
+    const int V = C >> 3;
+    const int64_t total = static_cast<int64_t>(N) * H * W * V;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int cv = static_cast<int>(i % V);
+        const int64_t pix = i / V;
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const int64_t n = pix / (static_cast<int64_t>(W) * H);
+        const __nv_bfloat16* s = dy + ((n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * 8;
+        float a[8], b[8], c[8], d[8];
+        load8(s, a);
+        load8(s + C, b);
+        load8(s + static_cast<int64_t>(2) * W * C, c);
+        load8(s + static_cast<int64_t>(2) * W * C + C, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = (a[j] + b[j]) + (c[j] + d[j]);
+        store8(dx + pix * C + cv * 8, a);
+    }
+}
+
+// ------------------------------------------------------------------ column sums (bias gradient)
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out /* [C] zeroed */,
+                              int64_t P, int C, int pix_per_chunk) {
+    extern __shared__ float sm[];  // [C]
+    const int V = C >> 3, R = blockDim.x / V;
+    const int cv = threadIdx.x % V, pr = threadIdx.x / V;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    if (pr < R) {
+        float s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = 0.f;
+        const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_chunk;
+        const int64_t p1 = min(P, p0 + pix_per_chunk);
+        for (int64_t p = p0 + pr; p < p1; p += R) {
+            float f[8];
+            load8(x + p * C + cv * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], s[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], sm[i]);
+}
+
+// ------------------------------------------------------------------ wgrad split reduction
+// grad[co][ci][tap_src] (+)= sum_s partial[s][co][slot*C64 + ci]   (OIHW fp32; slot -> tap via tapmap;
+// several slots may map to the same tap when weights were folded)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int ksplit, int Cout,
+                                    int CoutPad, int Cin, int T, int nslots, int C64,
+                                    const int* __restrict__ tapmap, int accumulate) {
+    const int64_t total = static_cast<int64_t>(Cout) * Cin * T;
+    const int64_t ld = static_cast<int64_t>(nslots) * C64;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        // ci fastest: coalesced reads of the (ksplit x larger) partial buffer, strided 4-byte writes
+        const int ci = static_cast<int>(i % Cin);
+        const int tap = static_cast<int>((i / Cin) % T);
+        const int co = static_cast<int>(i / (static_cast<int64_t>(T) * Cin));
+        float acc = 0.f;
+        bool any = false;
+        for (int slot = 0; slot < nslots; ++slot) {
+            if (tapmap[slot] != tap) continue;
+            any = true;
+            for (int s = 0; s < ksplit; ++s)
+                acc += partial[(static_cast<int64_t>(s) * CoutPad + co) * ld + static_cast<int64_t>(slot) * C64 + ci];
+        }
+        const int64_t o = (static_cast<int64_t>(co) * Cin + ci) * T + tap;
+        if (any || !accumulate) grad[o] = accumulate ? grad[o] + acc : acc;
+    }
+}
+
+static inline int gs_blocks(int64_t total, int threads) {
+    int64_t b = (total + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(num_sms() > 0 ? num_sms() : 148) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+// thread-block shape for the "fixed channel vector" kernels
+static inline int cv_threads(int C) {
+    const int V = C / 8;
+    int t = (256 / V) * V;
+    if (t < V) t = V;
+    return t;
+}
+static inline void cv_grid(int HW, int C, int N, int& chunks, int& pix_per_chunk) {
+    const int V = C / 8;
+    const int T = cv_threads(C);
+    const int R = T / V > 0 ? T / V : 1;
+    // aim for >= 4 waves of 148 SMs overall, but at least 4 row-iterations per thread
+    int want = (148 * 8 + N - 1) / N;
+    int ppc = (HW + want - 1) / want;
+    const int min_ppc = R * 4;
+    if (ppc < min_ppc) ppc = min_ppc;
+    ppc = ((ppc + R - 1) / R) * R;
+    pix_per_chunk = ppc;
+    chunks = (HW + ppc - 1) / ppc;
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" {
+
+int vqb_pack_weights(const float* w, void* out, int Cout, int Cin, int T, int nslots, const int* tapmap_dev,
+                     int transpose, int Kpad, void* stream) {
+    VQB_CHECK(w && out && tapmap_dev, "vqb_pack_weights: null pointer");
+    VQB_CHECK(Kpad % 8 == 0 && Kpad >= (transpose ? Cout : Cin), "vqb_pack_weights: bad Kpad=%d", Kpad);
+    const int R = transpose ? Cin : Cout;
+    const int64_t total = static_cast<int64_t>(R) * nslots * Kpad;
+    pack_weights_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(out), Cout, Cin, T, nslots, tapmap_dev, transpose, Kpad, 0);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+int vqb_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cpad, const float* shift,
+                     const float* inv_scale, void* stream) {
+    VQB_CHECK(x && y && Cpad % 8 == 0 && Cpad >= C, "vqb_nchw_to_nhwc: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * H * W;
+    nchw_to_nhwc_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<__nv_bfloat16*>(y), N, C, H * W, Cpad, shift, inv_scale);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+int vqb_nhwc_to_nchw(const void* g, float* gx, int N, int C, int H, int W, int Cpad, const float* inv_scale,
+                     void* stream) {
+    VQB_CHECK(g && gx && Cpad % 8 == 0 && Cpad >= C, "vqb_nhwc_to_nchw: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * H * W;
+    nhwc_to_nchw_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(g), gx, N, C, H * W, Cpad, inv_scale);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+// GroupNorm(+SiLU) forward. ws: >= N*C*2 doubles (zeroed here); mr: [N][G][2] floats (mean, rstd) kept for backward.
+int vqb_gn_silu_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mr, double* ws, int N,
+                    int HW, int C, int G, float eps, int silu, void* stream) {
+    VQB_CHECK(x && y && gamma && beta && mr && ws, "vqb_gn_silu_fwd: null pointer");
+    VQB_CHECK(C % 8 == 0 && C % G == 0 && C <= 2048, "vqb_gn_silu_fwd: C=%d G=%d unsupported", C, G);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VQB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * C, st));
+    int chunks, ppc;
+    cv_grid(HW, C, N, chunks, ppc);
+    const int T = cv_threads(C);
+    gn_stats_kernel<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x), ws, HW, C,
+                                                                        ppc);
+    gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(ws, mr, N, C, G, HW, eps);
+    gn_apply_kernel<<<dim3(chunks, N), T, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                   static_cast<__nv_bfloat16*>(y), mr, gamma, beta, HW, C, G, ppc,
+                                                   silu);
+    VQB_CUDA(cudaGetLastError());
+    count_launch(3);
+    return VQB_OK;
+}
+
+// GroupNorm(+SiLU) backward. ws: >= N*C*2 + N*G*2 floats. dx may alias dy. add (optional) is summed into dx.
+int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
+                    const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
+                    void* stream) {
+    VQB_CHECK(x && dy && dx && gamma && beta && mr && dgamma && dbeta && ws, "vqb_gn_silu_bwd: null pointer");
+    VQB_CHECK(C % 8 == 0 && C % G == 0 && C <= 2048, "vqb_gn_silu_bwd: C=%d G=%d unsupported", C, G);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* cs = ws;
+    float* gsum = ws + static_cast<int64_t>(N) * C * 2;
+    VQB_CUDA(cudaMemsetAsync(cs, 0, sizeof(float) * 2 * N * C, st));
+    int chunks, ppc;
+    cv_grid(HW, C, N, chunks, ppc);
+    const int T = cv_threads(C);
+    gn_bwd_reduce_kernel<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mr, gamma, beta, cs, HW, C, G,
+        ppc, silu);
+    const int fin = (N * G > C ? N * G : C);
+    gn_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(cs, gamma, gsum, dgamma, dbeta, N, C, G, HW);
+    gn_bwd_apply_kernel<<<dim3(chunks, N), T, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
+        static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), mr, gsum, gamma, beta, HW, C, G, ppc,
+        silu);
+    VQB_CUDA(cudaGetLastError());
+    count_launch(3);
+    return VQB_OK;
+}
+
+int vqb_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+    VQB_CHECK(x && y && C % 8 == 0, "vqb_upsample2x_fwd: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * H * W * (C / 8);
+    upsample2x_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), N, H, W, C);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+int vqb_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
+    VQB_CHECK(dy && dx && C % 8 == 0, "vqb_upsample2x_bwd: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * H * W * (C / 8);
+    upsample2x_bwd_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), N, H, W, C);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+// out[c] = sum over P pixels of x[p][c]  (bias gradient). out is overwritten.
+int vqb_colsum(const void* x, float* out, int64_t P, int C, void* stream) {
+    VQB_CHECK(x && out && C % 8 == 0 && C <= 2048, "vqb_colsum: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VQB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+    const int V = C / 8, T = cv_threads(C), R = T / V;
+    int64_t ppc = (P + 148 * 8 - 1) / (148 * 8);
+    if (ppc < R * 4) ppc = R * 4;
+    ppc = ((ppc + R - 1) / R) * R;
+    const int chunks = static_cast<int>((P + ppc - 1) / ppc);
+    colsum_kernel<<<chunks, T, C * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x), out, P, C,
+                                                        static_cast<int>(ppc));
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+int vqb_wgrad_reduce(const float* partial, float* grad, int ksplit, int Cout, int CoutPad, int Cin, int T, int nslots,
+                     int C64, const int* tapmap_dev, int accumulate, void* stream) {
+    VQB_CHECK(partial && grad && tapmap_dev, "vqb_wgrad_reduce: null pointer");
+    const int64_t total = static_cast<int64_t>(Cout) * Cin * T;
+    wgrad_reduce_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        partial, grad, ksplit, Cout, CoutPad, Cin, T, nslots, C64, tapmap_dev, accumulate);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+}  // extern "C"

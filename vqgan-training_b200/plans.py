@@ -1,0 +1,136 @@
+"""Geometry descriptors (views + taps) for every convolution variant on the hot path.
+
+A "plan" is a filled VqbConvDesc / VqbWgradDesc plus the tap map used to pack the OIHW fp32 master
+weights into the bf16 [rows][slot][K] matrix the tcgen05 kernels read. Plans depend only on shapes
+and are cached by the modules.
+
+Variants (reference call sites):
+  s1      : k x k stride-1 "same" conv (3x3 p1, 1x1 p0)                ae.py:105-117, VGG utils.py:95-111
+  s2      : 3x3 stride-2 conv after F.pad(0,1,0,1)  (Downsample)       ae.py:143-154
+  patch   : k x k stride-k non-overlapping conv (PatchD heads)         utils.py:156-185
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Tuple
+
+from native import VqbConvDesc, VqbTap, VqbView, VqbWgradDesc, dense_view
+
+
+def cpad(c: int) -> int:
+    """Internal NHWC channel count: multiple of 8 (16-byte pixel rows)."""
+    return (c + 7) // 8 * 8
+
+
+@dataclass
+class ConvGeom:
+    """Views/taps of the A operand for out-grid (N, Ho, Wo); tapmap[slot] = source tap in the KHxKW kernel."""
+    N: int
+    Ho: int
+    Wo: int
+    C: int  # channels of the A tensor (padded)
+    views: List[VqbView] = field(default_factory=list)
+    taps: List[Tuple[int, int, int]] = field(default_factory=list)  # (view, dw, dh)
+    tapmap: List[int] = field(default_factory=list)
+
+
+def geom_s1(N, H, W, C, k) -> ConvGeom:
+    p = (k - 1) // 2
+    g = ConvGeom(N, H, W, C, [dense_view(N, H, W, C)])
+    for kh in range(k):
+        for kw in range(k):
+            g.taps.append((0, kw - p, kh - p))
+            g.tapmap.append(kh * k + kw)
+    return g
+
+
+def geom_s1_dgrad(N, H, W, Cout_pad, k) -> ConvGeom:
+    """dgrad of a stride-1 same conv = same conv over dy with rotated taps (weights packed transposed)."""
+    p = (k - 1) // 2
+    g = ConvGeom(N, H, W, Cout_pad, [dense_view(N, H, W, Cout_pad)])
+    for kh in range(k):
+        for kw in range(k):
+            # slot (kh,kw) reads dy at (h + kh - p, w + kw - p) and uses source tap (k-1-kh, k-1-kw)
+            g.taps.append((0, kw - p, kh - p))
+            g.tapmap.append((k - 1 - kh) * k + (k - 1 - kw))
+    return g
+
+
+def geom_s2(N, H, W, C) -> ConvGeom:
+    """3x3 stride-2 conv over x padded by one zero row/col at bottom/right: out (H/2, W/2).
+    Tap (kh,kw) reads x[2ho+kh, 2wo+kw] = parity view (kh&1, kw&1) at (ho + kh//2, wo + kw//2)."""
+    assert H % 2 == 0 and W % 2 == 0, "Downsample needs even H, W"
+    g = ConvGeom(N, H // 2, W // 2, C)
+    for ph in range(2):
+        for pw in range(2):
+            g.views.append(VqbView(offset=(ph * W + pw) * C, Wv=W // 2, Hv=H // 2, Nv=N, _pad=0, sw=2 * C,
+                                   sh=2 * W * C, sn=H * W * C))
+    for kh in range(3):
+        for kw in range(3):
+            g.taps.append(((kh & 1) * 2 + (kw & 1), kw // 2, kh // 2))
+            g.tapmap.append(kh * 3 + kw)
+    return g
+
+
+def geom_s2_dgrad_classes(N, H, W, Cout_pad):
+    """dgrad of the stride-2 conv, one small conv per output parity class (ph,pw) of dx (H x W):
+    dx[2a+ph, 2b+pw] = sum over taps with kh%2==ph, kw%2==pw of dy[a - (kh-ph)/2, b - (kw-pw)/2] * W[kh,kw].
+    Returns [(ph, pw, ConvGeom over dy grid (N, H/2, W/2))]."""
+    out = []
+    Ho, Wo = H // 2, W // 2
+    for ph in range(2):
+        for pw in range(2):
+            g = ConvGeom(N, Ho, Wo, Cout_pad, [dense_view(N, Ho, Wo, Cout_pad)])
+            for kh in range(ph, 3, 2):
+                for kw in range(pw, 3, 2):
+                    g.taps.append((0, -((kw - pw) // 2), -((kh - ph) // 2)))
+                    g.tapmap.append(kh * 3 + kw)
+            out.append((ph, pw, g))
+    return out
+
+
+def geom_patch(N, H, W, C, k) -> ConvGeom:
+    """k x k stride-k conv: out (H/k, W/k); tap (kh,kw) has its own strided view."""
+    assert H % k == 0 and W % k == 0
+    g = ConvGeom(N, H // k, W // k, C)
+    for kh in range(k):
+        for kw in range(k):
+            g.views.append(VqbView(offset=(kh * W + kw) * C, Wv=W // k, Hv=H // k, Nv=N, _pad=0, sw=k * C,
+                                   sh=k * W * C, sn=H * W * C))
+            g.taps.append((kh * k + kw, 0, 0))
+            g.tapmap.append(kh * k + kw)
+    return g
+
+
+def conv_desc(g: ConvGeom, Cout: int, out_strides, flags=0, out_f32=False) -> VqbConvDesc:
+    """out_strides = (on, oh, ow, oc) in elements."""
+    d = VqbConvDesc()
+    d.C, d.Cout, d.N, d.H, d.W = g.C, Cout, g.N, g.Ho, g.Wo
+    d.nviews, d.ntaps, d.flags, d.out_f32 = len(g.views), len(g.taps), flags, 1 if out_f32 else 0
+    d.on, d.oh, d.ow, d.oc = out_strides
+    for i, v in enumerate(g.views):
+        d.views[i] = v
+    for i, (v, dw, dh) in enumerate(g.taps):
+        d.taps[i] = VqbTap(view=v, dw=dw, dh=dh, _pad=0)
+    return d
+
+
+def nhwc_strides(H, W, Cs):
+    return (H * W * Cs, W * Cs, Cs, 1)
+
+
+def nchw_strides(C, H, W):
+    return (C * H * W, W, 1, H * W)
+
+
+def wgrad_desc(g: ConvGeom, Cout_pad: int, ksplit: int) -> VqbWgradDesc:
+    """x operand geometry = forward geometry g; dy is the dense (N, Ho, Wo, Cout_pad) tensor."""
+    d = VqbWgradDesc()
+    d.C, d.Cout, d.N, d.H, d.W = g.C, Cout_pad, g.N, g.Ho, g.Wo
+    d.nviews, d.ntaps, d.ksplit = len(g.views), len(g.taps), ksplit
+    d.dy_view = dense_view(g.N, g.Ho, g.Wo, Cout_pad)
+    for i, v in enumerate(g.views):
+        d.views[i] = v
+    for i, (v, dw, dh) in enumerate(g.taps):
+        d.taps[i] = VqbTap(view=v, dw=dw, dh=dh, _pad=0)
+    return d
