@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: images/sec of the full training step (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference arithmetic on the box's host cores
+
+Workload (BASELINE.json configs[1]): FLUX-VAE config ch=128, ch_mult=1,2,4,4, z=16, 256x256 synthetic images,
+one step = Encoder -> clamp -> reg -> Decoder -> GradNorm -> LPIPS(eval) + 0.1*mean(z^2) (+ pooled L1 at the reference's
+HEAD weight 0.0) -> backward -> gradient all-reduce -> AdamW (vae_trainer.py:530-708), bf16 storage / fp32 accumulate.
+One process per GPU (torchrun for N > 1), weak scaling: per-GPU batch fixed.
+
+Printed JSON (one line, rank 0): see the contract in the task statement. `value` = device-resident inputs, CUDA-event
+timed, max over ranks; `e2e` = the same step through the public Trainer API with pinned host batches (H2D inside the timed
+region) and a device->host read of the loss every step; `roofline` = achieved tensor throughput of the dominant kernel
+(vqb::conv_gemm_kernel, fwd + dgrad launches) from CUDA events around every launch of an extra profiled step;
+`cpu_baseline` = the CPU oracle (port of the reference arithmetic) on this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "vqgan-training_b200")
+sys.path.insert(0, PKG)
+sys.path.insert(1, ROOT)
+os.environ.setdefault("VQB_OFFLINE", "1")
+os.environ.setdefault("WANDB_MODE", "disabled")
+
+import warnings
+
+warnings.simplefilter("ignore")
+
+import torch
+import torch.distributed as dist
+
+CFG = dict(vae_ch=128, vae_ch_mult="1,2,4,4", vae_z_channels=16, vae_num_res_blocks=2, resolution=256)
+# algorithmic conv FLOPs per image of one training step (SURVEY.md §8a / BASELINE.md §3): fwd + dgrad + wgrad of the VAE,
+# 2 LPIPS VGG forwards + 1 dgrad
+TFLOP_PER_IMAGE = 2.780
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    return 1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_step_runner(batch=1, threads=None):
+    """The reference arithmetic on host cores: oracle restatement (fp32, torch CPU) of one training step incl. AdamW."""
+    from oracle import lpips_oracle as LP
+    from oracle import seeded
+    from oracle import step_oracle as SO
+    from oracle import vae_oracle as VO
+
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = VO.VAEConfig(resolution=256, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16)
+    g = torch.Generator().manual_seed(42)
+    vsd = {}
+    for k, shp in VO.state_dict_shapes(cfg).items():
+        fan = max(1, int(torch.tensor(shp[1:]).prod())) if len(shp) == 4 else 1
+        if len(shp) == 4:
+            v = torch.randn(shp, generator=g) * (1.0 / fan) ** 0.5
+        elif k.endswith("weight"):
+            v = torch.ones(shp)
+        else:
+            v = torch.zeros(shp)
+        vsd[k] = v.requires_grad_(True)
+    lsd = {}
+    for k, shp in LP.lpips_state_dict_shapes().items():
+        if "scaling" in k:
+            continue
+        fan = max(1, int(torch.tensor(shp[1:]).prod())) if len(shp) == 4 else 1
+        lsd[k] = (torch.randn(shp, generator=g) * (2.0 / fan) ** 0.5) if len(shp) == 4 and "lin" not in k else \
+            (torch.rand(shp, generator=g) / fan if len(shp) == 4 else torch.zeros(shp))
+    opt = torch.optim.AdamW([p for p in vsd.values()], lr=1e-5 / 128, weight_decay=1e-3, betas=(0.9, 0.95))
+    real = torch.rand(batch, 3, 256, 256, generator=g) * 2 - 1
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        SO.generator_step(vsd, lsd, None, real, cfg, do_clamp=True, do_ganloss=False)
+        opt.step()
+
+    return step, batch
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU arithmetic (oracle port; the Python reference tree itself cannot travel to
+    the GPU box) on this box's host cores, same metric/unit/config. Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    step, b = cpu_step_runner(batch=1, threads=threads)
+    for _ in range(max(0, min(args.warmup, 1))):
+        step()
+    k = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = (time.perf_counter() - t0) / k
+    val = b / dt
+    line = {"metric": "images/sec", "value": val, "unit": "images/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": k, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "FLUX-VAE ch=128 mult 1,2,4,4 z=16 256x256 train step (VAE+LPIPS+z-loss+AdamW)",
+                       "per_gpu_batch": b, "note": "CPU oracle port of the reference arithmetic, batch 1 per step"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"{k} timed training steps at batch 1 (fwd+bwd+AdamW), torch CPU fp32"},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def profile_conv_kernels(tr, batch_dev):
+    """One extra (untimed) step with CUDA events around every conv_gemm / wgrad_gemm launch on the launching stream."""
+    import ops
+
+    rec = {"conv": [], "wgrad": []}
+    orig_conv, orig_wgrad = ops.run_conv_gemm, ops.run_wgrad
+
+    def flops_conv(g, Cout):
+        return 2.0 * g.N * g.Ho * g.Wo * Cout * g.C * len(g.taps)
+
+    def conv_wrap(g, a, wp, Cout, out, out_strides, *aa, **kk):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_conv(g, a, wp, Cout, out, out_strides, *aa, **kk)
+        e1.record()
+        rec["conv"].append((e0, e1, flops_conv(g, Cout)))
+        return r
+
+    def wgrad_wrap(g, x, dy, weight_shape, Cout_pad):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_wgrad(g, x, dy, weight_shape, Cout_pad)
+        e1.record()
+        Cout, Cin, KH, KW = weight_shape
+        rec["wgrad"].append((e0, e1, 2.0 * g.N * g.Ho * g.Wo * Cout * Cin * KH * KW))
+        return r
+
+    ops.run_conv_gemm, ops.run_wgrad = conv_wrap, wgrad_wrap
+    try:
+        tr.step(batch_dev)
+        torch.cuda.synchronize()
+    finally:
+        ops.run_conv_gemm, ops.run_wgrad = orig_conv, orig_wgrad
+    out = {}
+    for k, lst in rec.items():
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in lst)
+        fl = sum(f for _, _, f in lst)
+        out[k] = {"launches": len(lst), "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0,
+                  "flops_per_launch": fl / max(1, len(lst)), "ms_per_launch": ms / max(1, len(lst))}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("VQB_BENCH_BATCH", "32")), help="per-GPU batch")
+    ap.add_argument("--gan", action="store_true", help="configs[2]: + PatchDiscriminator hinge + GradNorm + LeCam")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import native
+    import vae_trainer as vt
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA (sm_100a) device: there is no CPU path"
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    W = max(3, args.warmup)
+    K = args.steps
+    B, R = args.batch, CFG["resolution"]
+
+    tr = vt.Trainer(device, vae_resolution=R, vae_ch=CFG["vae_ch"], vae_ch_mult=CFG["vae_ch_mult"],
+                    vae_num_res_blocks=CFG["vae_num_res_blocks"], vae_z_channels=CFG["vae_z_channels"], do_clamp=True,
+                    do_ganloss=args.gan, disc_type="hinge", use_lecam=args.gan, max_steps=100000, lpips_eval=True)
+    loader = vt.SyntheticLoader(B, R, seed=42 + rank, n_distinct=4)
+    host_batches = loader.batches
+    dev_batches = [b.to(device) for b in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up
+    for i in range(W):
+        tr.step(dev_batches[i % len(dev_batches)])
+    barrier()
+
+    # ---------------- timed: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        out = tr.step(dev_batches[i % len(dev_batches)])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    launches = (native.launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- timed: end to end (pinned host batch -> H2D inside, loss read back every step)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last_loss = 0.0
+    for i in range(K):
+        o = tr.step(host_batches[i % len(host_batches)])
+        last_loss = float(o["overall_vae_loss"])  # device -> host read of the step's result
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / K
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    prof = profile_conv_kernels(tr, dev_batches[0]) if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = world * B / (ms * 1e-3)
+        e2e = world * B / (ms_e2e * 1e-3)
+        line = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "FLUX-VAE ch=128 ch_mult=1,2,4,4 z=16 256x256: Encoder->clamp->Decoder->GradNorm->"
+                                   "LPIPS(eval)+0.1*mean(z^2)" + ("+PatchD hinge+LeCam" if args.gan else "") +
+                                   " fwd+bwd+grad all-reduce+AdamW (BASELINE.json configs[%d])" % (2 if args.gan else 1),
+                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "no explicit flush: per-step working set (activations ~0.9 GB/image) >> 126 MB L2",
+                       "tflop_per_image": TFLOP_PER_IMAGE},
+            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 3 * R * R * 4,
+                    "d2h_bytes_per_step": 4, "last_loss": last_loss},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "achieved_step_tflops_per_gpu": TFLOP_PER_IMAGE * B / (ms * 1e-3),
+            "step_frac_of_peak": TFLOP_PER_IMAGE * B / (ms * 1e-3) / peak,
+            "roofline": {"kernel": "vqb::conv_gemm_kernel (tcgen05 implicit-GEMM conv, fwd+dgrad launches of one step)",
+                         "bound": "tensor", "achieved": prof["conv"]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                         "frac": prof["conv"]["tflops"] / peak, "traffic": None, "peak_source": peak_src,
+                         "launches_per_step": prof["conv"]["launches"], "ms_per_step": prof["conv"]["ms"],
+                         "alg_flops_per_launch": prof["conv"]["flops_per_launch"],
+                         "avg_launch_ms": prof["conv"]["ms_per_launch"]},
+            "roofline_wgrad": {"kernel": "vqb::wgrad_gemm_kernel (+ split reduction)", "bound": "tensor",
+                               "achieved": prof["wgrad"]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                               "frac": prof["wgrad"]["tflops"] / peak, "launches_per_step": prof["wgrad"]["launches"],
+                               "ms_per_step": prof["wgrad"]["ms"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            step, b = cpu_step_runner(batch=1, threads=threads)
+            step()
+            t0 = time.perf_counter()
+            n = 2
+            for _ in range(n):
+                step()
+            dt = (time.perf_counter() - t0) / n
+            line["cpu_baseline"] = {"value": b / dt, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n} training steps at batch 1 of the same workload (oracle port of the "
+                                              f"reference arithmetic, torch CPU fp32, {threads} threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,69 @@ typedef struct VqbWgradDesc {
 
 int vqb_wgrad_gemm(const VqbWgradDesc* d, const void* dy, const void* x, float* partial, void* stream);
 
+/* number of fp32 columns per Cout row of the wgrad partial buffer: ntaps * roundup(C, 64) */
+int vqb_wgrad_cols(int ntaps, int C);
+
+/*
+ * grad[co][ci][tap] (OIHW fp32) (+)= sum_s partial[s][co][slot*C64 + ci], slot -> tap through tapmap_dev (int32[nslots],
+ * device memory). Deterministic (no atomics). Replaces the tail of aten::convolution_backward (weight gradient layout).
+ */
+int vqb_wgrad_reduce(const float* partial, float* grad, int ksplit, int Cout, int CoutPad, int Cin, int T, int nslots,
+                     int C64, const int* tapmap_dev, int accumulate, void* stream);
+
+/*
+ * OIHW fp32 master weights -> bf16 [R][nslots][Kpad] GEMM operand (R = Cin if transpose else Cout; transpose = dgrad
+ * layout; tapmap_dev selects / reorders filter taps, e.g. the 180-degree rotation of the data gradient).
+ * Replaces: the per-step fp32->bf16 weight casts of torch.autocast (vae_trainer.py:453,623) and cuDNN's internal
+ * filter transforms.
+ */
+int vqb_pack_weights(const float* w_oihw, void* out, int Cout, int Cin, int T, int nslots, const int* tapmap_dev,
+                     int transpose, int Kpad, void* stream);
+
+/*
+ * Module-boundary layout conversion. y[n,h,w,c] = (x[n,c,h,w] - shift[c]) * inv_scale[c] as bf16 NHWC with Cpad
+ * channels (pad = 0); shift/inv_scale may be NULL. The scaled form is LPIPS/PatchD ScalingLayer (utils.py:70-71).
+ * vqb_nhwc_to_nchw is the inverse / the backward of it (gx = g * inv_scale).
+ */
+int vqb_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cpad, const float* shift,
+                     const float* inv_scale, void* stream);
+int vqb_nhwc_to_nchw(const void* g, float* gx, int N, int C, int H, int W, int Cpad, const float* inv_scale,
+                     void* stream);
+
+/*
+ * FP32GroupNorm (+ swish) forward / backward on bf16 NHWC: 32 groups, biased variance, eps inside the sqrt, fp32
+ * statistics (ae.py:41-53 + ae.py:13-14). mr = [N][G][2] (mean, rstd) kept for the backward.
+ * fwd workspace ws: N*C*2 doubles; bwd workspace ws: N*C*2 + N*G*2 floats. `add` (optional) is summed into dx.
+ */
+int vqb_gn_silu_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mr, double* ws, int N,
+                    int HW, int C, int G, float eps, int silu, void* stream);
+int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
+                    const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
+                    void* stream);
+
+/* nearest-neighbour x2 up-sampling (ae.py:165) and its backward (2x2 sum), bf16 NHWC */
+int vqb_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int vqb_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+
+/* out[c] = sum over P pixels of x[p][c] : Conv2d bias gradient */
+int vqb_colsum(const void* x, float* out, int64_t P, int C, void* stream);
+
+/*
+ * 2x2/2 max-pool of the VGG16 trunk (torchvision features[4,9,16,23]) and its backward: first-maximum tie rule of
+ * ATen; relu_mask additionally gates by x > 0 (x is a post-ReLU activation); `add` (optional) is summed into dx.
+ */
+int vqb_maxpool2_fwd(const void* x, void* y, int N, int Ho, int Wo, int C, void* stream);
+int vqb_maxpool2_bwd(const void* x, const void* dy, const void* add, void* dx, int N, int Ho, int Wo, int C,
+                     int relu_mask, void* stream);
+
+/*
+ * One LPIPS layer (utils.py:44-53,134-140): out[n] += mean_p sum_c w[c] (f0/(|f0|+1e-10) - f1/(|f1|+1e-10))^2,
+ * and its backward w.r.t. f0 only (frozen trunk, target branch carries no gradient), gated by f0 > 0.
+ */
+int vqb_lpips_tail_fwd(const void* f0, const void* f1, const float* w, float* out, int N, int HW, int C, void* stream);
+int vqb_lpips_tail_bwd(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW, int C,
+                       void* stream);
+
 /* library / device info */
 const char* vqb_last_error(void);
 int vqb_version(void);

@@ -38,9 +38,10 @@ def lpips_key(s, ci):  # LPIPS: net.slice{s}.{idx}  (utils.py:92-111)
     return f"net.slice{s}.{ci}"
 
 
-def patchd_key(s, ci):  # PatchDiscriminator: slice{s}.0.{local idx}  (nn.Sequential(_vgg.features[a:b]), utils.py:150-154)
-    start = [0, 4, 9, 16, 23][s - 1]
-    return f"slice{s}.0.{ci - start}"
+def patchd_key(s, ci):
+    # PatchDiscriminator: nn.Sequential(_vgg.features[a:b]) (utils.py:150-154); slicing a Sequential keeps the
+    # ORIGINAL module names, so the key is slice{s}.0.{torchvision idx}
+    return f"slice{s}.0.{ci}"
 
 
 def normalize_tensor(x, eps=1e-10):  # utils.py:134-136 (eps added AFTER the sqrt)

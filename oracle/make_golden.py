@@ -1,0 +1,260 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on seeded weights/inputs.
+TEST INFRASTRUCTURE. Runs only in the build container (the reference tree is not on the GPU box); the produced
+fixtures are committed. At generation time the oracle restatement is also checked against the reference, so a
+fixture is never written from a disagreeing pair.
+
+    python oracle/make_golden.py            # writes tests/golden/
+
+Stubs needed to import the reference here: `webdataset` (not installed; only
+create_dataloader uses it), torchvision.models.vgg16 -> weights=None (no network), LPIPS.load_from_pretrained -> no-op
+(vgg.pth unreachable, and its fallback NameErrors on the missing `import os`), single-rank gloo group for GradNorm.
+"""
+import os
+import sys
+import types
+
+sys.dont_write_bytecode = True
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("VQB_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(1, REPO)
+sys.modules["webdataset"] = types.ModuleType("webdataset")
+os.environ["WANDB_MODE"] = "disabled"
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torchvision.models as M
+
+_vgg16 = M.vgg16
+M.vgg16 = lambda pretrained=False, **kw: _vgg16(weights=None)
+import utils as ref_utils  # noqa: E402  (the reference's utils.py)
+
+ref_utils.LPIPS.load_from_pretrained = lambda self, name="vgg_lpips": None
+import ae as ref_ae  # noqa: E402
+import vae_trainer as ref_vt  # noqa: E402
+
+from oracle import loss_oracle as LO  # noqa: E402
+from oracle import lpips_oracle as LP  # noqa: E402
+from oracle import seeded  # noqa: E402
+from oracle import step_oracle as SO  # noqa: E402
+from oracle import vae_oracle as VO  # noqa: E402
+
+torch.set_grad_enabled(True)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+OUT = os.path.join(REPO, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", RANK="0", WORLD_SIZE="1")
+dist.init_process_group("gloo")
+
+
+def close(a, b, tol, what):
+    a, b = torch.as_tensor(a).detach().double(), torch.as_tensor(b).detach().double()
+    diff = (a - b).norm().item()
+    # mathematically-zero gradients (a conv bias in front of a 1-channel-per-group GroupNorm) are pure rounding noise
+    floor = 1e-6 * (b.numel() ** 0.5)
+    assert diff <= tol * b.norm().item() + floor, \
+        f"oracle disagrees with reference on {what}: |a-b|={diff:.3e} |b|={b.norm().item():.3e}"
+    return diff
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                        **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print("wrote", name, {k: tuple(np.asarray(v.detach() if torch.is_tensor(v) else v).shape) for k, v in arrs.items()})
+
+
+def vae_case(name, cfg: VO.VAEConfig, N, R, with_attn=False):
+    ref = ref_ae.VAE(resolution=cfg.resolution, in_channels=cfg.in_channels, ch=cfg.ch, out_ch=cfg.out_ch,
+                     ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, z_channels=cfg.z_channels,
+                     use_attn=False, decoder_also_perform_hr=cfg.decoder_also_perform_hr, use_wavelet=False)
+    if with_attn:  # the reference cannot construct use_attn=True at HEAD (ae.py:233-235); AttnBlock itself works
+        c = cfg.ch * cfg.ch_mult[-1]
+        ref.encoder.mid.attn_1 = ref_ae.AttnBlock(c)
+        ref.decoder.mid.attn_1 = ref_ae.AttnBlock(cfg.ch * cfg.dec_ch_mult[-1])
+    sd = seeded.fill_state_dict(ref.state_dict(), name)
+    # residual branches must matter in a parity test: conv2 is ~0 at the reference's init (ae.py:120)
+    ref.load_state_dict(sd)
+    x = seeded.tensor(name + "/x", (N, cfg.in_channels, R, R), 1.0, "uniform")
+    dec, z = ref(x)
+    loss = dec.pow(2).mean() + z.pow(2).mean()
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    # oracle
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    odec, oz = VO.vae_forward(osd, x, cfg)
+    oloss = odec.pow(2).mean() + oz.pow(2).mean()
+    oloss.backward()
+    close(oz, z, 1e-5, name + " z")
+    close(odec, dec, 1e-5, name + " dec")
+    for k in grads:
+        close(osd[k].grad, grads[k], 1e-4, name + " grad " + k)
+    keys = sorted(grads)
+    gn = np.array([grads[k].norm().item() for k in keys], dtype=np.float64)
+    pick = [k for k in keys if k in ("encoder.conv_in.weight", "decoder.conv_out.weight",
+                                     "encoder.down.0.downsample.conv.weight", "decoder.up.1.upsample.conv.weight",
+                                     "encoder.mid.block_1.norm1.weight", "decoder.mid.attn_1.qkv.weight")]
+    save(name, z=z, dec=dec, loss=loss, grad_keys=np.array(keys), grad_norms=gn,
+         **{"grad::" + k: grads[k] for k in pick})
+
+
+def lpips_case():
+    name = "lpips_small"
+    torch.manual_seed(0)
+    ref = ref_utils.LPIPS().eval()
+    sd = seeded.fill_state_dict(ref.state_dict(), "lpips")
+    ref.load_state_dict(sd)
+    a = seeded.tensor(name + "/a", (2, 3, 32, 32), 1.0, "uniform").requires_grad_(True)
+    b = seeded.tensor(name + "/b", (2, 3, 32, 32), 1.0, "uniform")
+    val = ref(a, b)
+    val.mean().backward()
+    a2 = a.detach().clone().requires_grad_(True)
+    oval = LP.lpips_forward(sd, a2, b)
+    oval.mean().backward()
+    close(oval, val, 1e-5, "lpips value")
+    close(a2.grad, a.grad, 1e-4, "lpips input grad")
+    save(name, val=val, grad_a=a.grad)
+
+
+def patchd_case():
+    name = "patchd_small"
+    torch.manual_seed(0)
+    ref = ref_utils.PatchDiscriminator()
+    sd = seeded.fill_state_dict(ref.state_dict(), "patchd")
+    ref.load_state_dict(sd)
+    x = seeded.tensor(name + "/x", (2, 3, 32, 32), 1.0, "uniform").requires_grad_(True)
+    y = ref(x)
+    (y * seeded.tensor(name + "/gy", y.shape)).sum().backward()
+    grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    osd = {k: v.clone().requires_grad_(torch.is_floating_point(v) and "scaling" not in k) for k, v in sd.items()}
+    x2 = x.detach().clone().requires_grad_(True)
+    oy = LP.patchd_forward(osd, x2)
+    (oy * seeded.tensor(name + "/gy", y.shape)).sum().backward()
+    close(oy, y, 1e-5, "patchd logits")
+    close(x2.grad, x.grad, 1e-4, "patchd input grad")
+    for k in grads:
+        close(osd[k].grad, grads[k], 1e-4, "patchd grad " + k)
+    keys = sorted(grads)
+    save(name, logits=y, grad_x=x.grad, grad_keys=np.array(keys),
+         grad_norms=np.array([grads[k].norm().item() for k in keys]),
+         **{"grad::" + k: grads[k] for k in ("binary_classifier1.0.weight", "binary_classifier5.0.weight",
+                                              "slice1.0.0.weight")})
+
+
+def losses_case():
+    name = "losses"
+    r = seeded.tensor(name + "/real", (4, 16))
+    f = seeded.tensor(name + "/fake", (4, 16))
+    out = {}
+    for dt in ("hinge", "bce"):
+        l, ar, af, acc = ref_vt.gan_disc_loss(r, f, dt)
+        ol, oar, oaf, oacc = LO.gan_disc_loss(r, f, dt)
+        close(ol, l, 1e-6, "gan_disc_loss " + dt)
+        assert abs(ar - oar) < 1e-6 and abs(af - oaf) < 1e-6 and abs(acc - oacc) < 1e-9
+        out[dt] = np.array([l.item(), ar, af, acc])
+    x = seeded.tensor(name + "/x", (2, 3, 32, 32), 1.0, "uniform")
+    xr = seeded.tensor(name + "/xr", (2, 3, 32, 32), 1.0, "uniform")
+    z = seeded.tensor(name + "/z", (2, 4, 8, 8))
+    vl, st = ref_vt.vae_loss_function(x, xr, z)
+    ovl, ost = LO.vae_loss_function(x, xr, z)
+    close(ovl, vl, 1e-6, "vae_loss_function")
+    for k in st:
+        assert abs(st[k] - ost[k]) < 1e-5, k
+    heat = ref_vt.blurriness_heatmap(x)
+    close(LO.blurriness_heatmap(x), heat, 1e-5, "blurriness_heatmap")
+    # low-pass branch of the recon loss (do_pool=False) works in the reference; the pooled branch crashes (fact 4)
+    vl2, st2 = ref_vt.vae_loss_function(x, xr, z, do_pool=False, do_recon=True)
+    ovl2, ost2 = LO.vae_loss_function(x, xr, z, do_pool=False, do_recon=True)
+    close(ovl2, vl2, 1e-6, "vae_loss lowpass")
+    assert abs(st2["recon_loss"] - ost2["recon_loss"]) < 1e-6
+    # GradNorm backward
+    g_in = seeded.tensor(name + "/gn_x", (2, 3, 8, 8)).requires_grad_(True)
+    gy = seeded.tensor(name + "/gn_gy", (2, 3, 8, 8))
+    (ref_vt.gradnorm(g_in, 0.5) * gy).sum().backward()
+    g2 = g_in.detach().clone().requires_grad_(True)
+    (LO.gradnorm(g2, 0.5) * gy).sum().backward()
+    close(g2.grad, g_in.grad, 1e-6, "gradnorm backward")
+    # wavelet
+    wv = ref_utils.wavelet_transform_multi_channel(x)
+    close(LP.wavelet_transform_multi_channel(x), wv, 1e-6, "wavelet")
+    save(name, hinge=out["hinge"], bce=out["bce"], vae_loss=vl, kl_loss=st["kl_loss"], abs_z=st["average_of_abs_z"],
+         std_abs_z=st["std_of_abs_z"], heat=heat, lowpass_recon=st2["recon_loss"], gradnorm_grad=g_in.grad, wavelet=wv)
+
+
+def step_case():
+    """Restates vae_trainer.py:530-708 around the reference's own modules/functions (train_ddp itself cannot run)."""
+    name = "step_small"
+    cfg = VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=4)
+    torch.manual_seed(0)
+    vae = ref_ae.VAE(resolution=32, in_channels=3, ch=32, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, z_channels=4,
+                     use_attn=False, decoder_also_perform_hr=False, use_wavelet=False)
+    vsd = seeded.fill_state_dict(vae.state_dict(), name + "/vae")
+    vae.load_state_dict(vsd)
+    lp = ref_utils.LPIPS().eval()
+    lsd = seeded.fill_state_dict(lp.state_dict(), "lpips")
+    lp.load_state_dict(lsd)
+    disc = ref_utils.PatchDiscriminator()
+    dsd = seeded.fill_state_dict(disc.state_dict(), "patchd")
+    disc.load_state_dict(dsd)
+    real = seeded.tensor(name + "/real", (2, 3, 32, 32), 1.0, "uniform")
+    res = {}
+    for gan in (False, True):
+        vae.zero_grad()
+        z = vae.encoder(real)
+        z = z.clamp(-8.0, 8.0)
+        z_s = vae.reg(z)
+        recon = vae.decoder(z_s)
+        percep = lp(ref_vt.gradnorm(recon), real).mean()
+        vl, _ = ref_vt.vae_loss_function(real, ref_vt.gradnorm(recon, weight=0.001), z)
+        if gan:
+            g = -disc(ref_vt.gradnorm(recon, weight=1.0)).mean()
+            loss = percep + g + vl
+        else:
+            loss = percep + vl
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in vae.named_parameters()}
+        osd = {k: v.clone().requires_grad_(True) for k, v in vsd.items()}
+        o = SO.generator_step(osd, lsd, dsd, real, cfg, do_clamp=True, do_ganloss=gan, disc_type="hinge")
+        close(o["loss"], loss, 1e-5, f"step loss gan={gan}")
+        for k in grads:
+            close(osd[k].grad, grads[k], 2e-4, f"step grad {k} gan={gan}")
+        keys = sorted(grads)
+        tag = "gan" if gan else "nogan"
+        res[tag + "_loss"] = loss.detach()
+        res[tag + "_percep"] = percep.detach()
+        res[tag + "_grad_norms"] = np.array([grads[k].norm().item() for k in keys])
+        res[tag + "_grad_conv_in"] = grads["encoder.conv_in.weight"]
+        res["grad_keys"] = np.array(keys)
+        res["recon"] = recon.detach()
+    # discriminator step (hinge + LeCam)
+    disc.zero_grad()
+    rp, fp = disc(real), disc(res["recon"])
+    dl, ar, af, acc = ref_vt.gan_disc_loss(rp, fp, "hinge")
+    lec = (rp - 0.05).pow(2).mean() + (fp - 0.1).pow(2).mean()
+    (dl.mean() + 0.1 * lec).backward()
+    dgr = {k: p.grad.detach().clone() for k, p in disc.named_parameters()}
+    osd = {k: v.clone().requires_grad_(torch.is_floating_point(v) and "scaling" not in k) for k, v in dsd.items()}
+    o = SO.discriminator_step(osd, real, res["recon"], "hinge", True, (0.1, 0.05))
+    close(o["d_loss"], dl.mean() + 0.1 * lec, 1e-5, "d step loss")
+    for k in dgr:
+        close(osd[k].grad, dgr[k], 2e-4, "d step grad " + k)
+    dkeys = sorted(dgr)
+    res["d_loss"] = (dl.mean() + 0.1 * lec).detach()
+    res["d_grad_keys"] = np.array(dkeys)
+    res["d_grad_norms"] = np.array([dgr[k].norm().item() for k in dkeys])
+    save(name, **res)
+
+
+if __name__ == "__main__":
+    vae_case("vae_small", VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=2, z_channels=4), 2, 32)
+    vae_case("vae_attn", VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=4,
+                                      use_attn=True), 2, 32, with_attn=True)
+    vae_case("vae_hr", VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=4,
+                                    decoder_also_perform_hr=True), 1, 32)
+    lpips_case()
+    patchd_case()
+    losses_case()
+    step_case()
+    dist.destroy_process_group()
+    print("all golden fixtures written to", OUT)

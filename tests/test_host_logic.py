@@ -1,0 +1,194 @@
+"""CPU: host-side logic above the C ABI — convolution geometry (views/taps/tap maps of plans.py) checked by emulating
+the kernel's documented semantics in PyTorch, drop-in surface (class names, state_dict keys, init parity with the
+reference when its tree is present), split-K heuristics, CLI flags."""
+import os
+import random
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import plans
+from oracle import lpips_oracle as LP
+from oracle import vae_oracle as VO
+
+
+def emulate_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: int):
+    """include/vqb200.h semantics of vqb_conv_gemm: out[n,h,w,co] = sum_t sum_c view_t[n,h+dh,w+dw,c] * wp[co][t][c],
+    reads outside a view are zero. a: flat fp32 buffer of the A tensor; wp [Cout][T][C]."""
+    out = torch.zeros(g.N, g.Ho, g.Wo, Cout)
+    flat = a.reshape(-1)
+    for t_i, (v, dw, dh) in enumerate(g.taps):
+        vw = g.views[v]
+        for n in range(g.N):
+            for h in range(g.Ho):
+                hh = h + dh
+                if not (0 <= hh < vw.Hv) or n >= vw.Nv:
+                    continue
+                for w in range(g.Wo):
+                    ww = w + dw
+                    if not (0 <= ww < vw.Wv):
+                        continue
+                    off = vw.offset + n * vw.sn + hh * vw.sh + ww * vw.sw
+                    out[n, h, w] += wp[:, t_i, :] @ flat[off:off + g.C]
+    return out
+
+
+def pack(w, tapmap, transpose):
+    Cout, Cin = w.shape[:2]
+    wt = w.reshape(Cout, Cin, -1)[:, :, tapmap]
+    return wt.permute(1, 2, 0).contiguous() if transpose else wt.permute(0, 2, 1).contiguous()
+
+
+def test_geom_s1_matches_conv2d():
+    torch.manual_seed(0)
+    x, w = torch.randn(2, 5, 6, 8), torch.randn(4, 8, 3, 3)
+    g = plans.geom_s1(2, 5, 6, 8, 3)
+    out = emulate_conv_gemm(g, x, pack(w, g.tapmap, False), 4)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(out, ref, atol=1e-4)
+
+
+def test_geom_s1_dgrad_matches_conv_transpose():
+    torch.manual_seed(1)
+    dy, w = torch.randn(1, 5, 4, 8), torch.randn(8, 3, 3, 3)  # w: [Cout=8, Cin=3]
+    g = plans.geom_s1_dgrad(1, 5, 4, 8, 3)
+    out = emulate_conv_gemm(g, dy, pack(w, g.tapmap, True), 3)
+    ref = F.conv_transpose2d(dy.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(out, ref, atol=1e-4)
+
+
+def test_geom_s2_matches_padded_stride2_conv():
+    """Downsample (ae.py:150-154): F.pad(x,(0,1,0,1)) then conv3x3 stride 2 — the pad is the view's zero fill."""
+    torch.manual_seed(2)
+    x, w = torch.randn(2, 6, 8, 8), torch.randn(5, 8, 3, 3)
+    g = plans.geom_s2(2, 6, 8, 8)
+    out = emulate_conv_gemm(g, x, pack(w, g.tapmap, False), 5)
+    ref = F.conv2d(F.pad(x.permute(0, 3, 1, 2), (0, 1, 0, 1)), w, stride=2).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and torch.allclose(out, ref, atol=1e-4)
+
+
+def test_geom_s2_dgrad_classes_cover_the_transposed_conv():
+    torch.manual_seed(3)
+    N, H, W, C, Co = 1, 6, 4, 8, 8
+    dy, w = torch.randn(N, H // 2, W // 2, Co), torch.randn(Co, C, 3, 3)
+    dx = torch.zeros(N, H, W, C)
+    for ph, pw, g in plans.geom_s2_dgrad_classes(N, H, W, Co):
+        dx[:, ph::2, pw::2, :] = emulate_conv_gemm(g, dy, pack(w, g.tapmap, True), C)
+    x = torch.zeros(N, C, H, W, requires_grad=True)
+    y = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, stride=2)
+    (ref,) = torch.autograd.grad(y, x, dy.permute(0, 3, 1, 2))
+    assert torch.allclose(dx, ref.permute(0, 2, 3, 1), atol=1e-4)
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_geom_patch_matches_strided_conv(k):
+    torch.manual_seed(4)
+    x, w = torch.randn(2, 8, 8, 8), torch.randn(3, 8, k, k)
+    g = plans.geom_patch(2, 8, 8, 8, k)
+    out = emulate_conv_gemm(g, x, pack(w, g.tapmap, False), 3)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, stride=k).permute(0, 2, 3, 1)
+    assert torch.allclose(out, ref, atol=1e-4)
+
+
+def test_cpad_and_desc_fields():
+    assert [plans.cpad(c) for c in (1, 3, 8, 9, 16, 128)] == [8, 8, 8, 16, 16, 128]
+    g = plans.geom_s2(2, 8, 8, 16)
+    d = plans.conv_desc(g, 32, plans.nhwc_strides(4, 4, 32), flags=3)
+    assert (d.C, d.Cout, d.N, d.H, d.W, d.nviews, d.ntaps, d.flags) == (16, 32, 2, 4, 4, 4, 9, 3)
+    assert d.views[3].offset == (8 + 1) * 16 and d.views[3].sw == 32 and d.views[3].sh == 2 * 8 * 16
+    wd = plans.wgrad_desc(g, 32, 4)
+    assert wd.dy_view.Wv == 4 and wd.ksplit == 4 and wd.ntaps == 9
+
+
+def test_ksplit_heuristic_bounds():
+    import ops
+
+    for (N, H, W, C, Co) in [(8, 256, 256, 128, 128), (8, 64, 64, 512, 512), (1, 4, 4, 64, 64), (2, 32, 32, 16, 512)]:
+        g = plans.geom_s1(N, H, W, C, 3)
+        ks = ops.choose_ksplit(g, Co)
+        assert 1 <= ks <= 512
+
+
+def test_dropin_surface_names_and_keys():
+    import ae
+    import utils
+    import vae_trainer as vt
+
+    for name in ("swish", "StandardizedC2d", "FP32GroupNorm", "AttnBlock", "ResnetBlock", "Downsample", "Upsample",
+                 "Encoder", "Decoder", "DiagonalGaussian", "VAE", "AutoEncoder"):
+        assert hasattr(ae, name), name
+    for name in ("LPIPS", "ScalingLayer", "NetLinLayer", "vgg16", "normalize_tensor", "spatial_average",
+                 "PatchDiscriminator", "prepare_filter", "wavelet_transform_multi_channel"):
+        assert hasattr(utils, name), name
+    for name in ("GradNormFunction", "gradnorm", "avg_scalar_over_nodes", "gan_disc_loss", "create_dataloader",
+                 "blurriness_heatmap", "vae_loss_function", "cleanup", "train_ddp"):
+        assert hasattr(vt, name), name
+    cfg = VO.VAEConfig(resolution=64, ch=32, ch_mult=(1, 2, 4), num_res_blocks=2, z_channels=8, use_attn=True)
+    m = ae.VAE(64, 3, 32, 3, [1, 2, 4], 2, 8, True, False, False)
+    sd = m.state_dict()
+    sh = VO.state_dict_shapes(cfg)
+    assert set(sd) == set(sh) and all(tuple(sd[k].shape) == tuple(sh[k]) for k in sh)
+    hr = ae.VAE(64, 3, 32, 3, [1, 2], 1, 4, False, True, False)
+    assert len(hr.decoder.up) == 3 and hr.decoder.ffactor == 4  # ch_mult + [4] (ae.py:381)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert set(utils.LPIPS().state_dict()) == set(LP.lpips_state_dict_shapes())
+        assert set(utils.PatchDiscriminator().state_dict()) == set(LP.patchd_state_dict_shapes())
+        assert all(not p.requires_grad for p in utils.LPIPS().parameters())
+
+
+def test_cli_flags_match_reference():
+    import vae_trainer as vt
+
+    names = {p.name: p for p in vt.train_ddp.params}
+    expected = {"dataset_url": "synthetic", "test_dataset_url": "synthetic", "num_epochs": 2, "batch_size": 8,
+                "do_ganloss": False, "learning_rate_vae": 1e-5, "learning_rate_disc": 2e-4, "vae_resolution": 256,
+                "vae_in_channels": 3, "vae_ch": 256, "vae_ch_mult": "1,2,4,4", "vae_num_res_blocks": 2,
+                "vae_z_channels": 16, "run_name": "run", "max_steps": 1000, "evaluate_every_n_steps": 250,
+                "load_path": None, "do_clamp": False, "clamp_th": 8.0, "max_spatial_dim": 256, "do_attn": False,
+                "decoder_also_perform_hr": False, "project_name": "vae_sweep_attn_lr_width", "crop_invariance": False,
+                "flip_invariance": False, "do_compile": False, "use_wavelet": False,
+                "augment_before_perceptual_loss": False, "downscale_factor": 16, "use_lecam": False,
+                "disc_type": "bce"}
+    assert set(names) == set(expected)
+    for k, v in expected.items():
+        assert names[k].default == v, k
+    assert names["do_ganloss"].is_flag and names["do_clamp"].is_flag
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ae.py")), reason="reference tree not present")
+def test_seeded_init_matches_reference_bit_for_bit():
+    """torch.manual_seed(s); VAE(...) must produce the reference's initial weights (same parameter creation order and
+    init calls). Runs only where /root/reference exists (the build container)."""
+    import subprocess
+
+    code = f"""
+import sys, types, torch
+sys.dont_write_bytecode = True
+sys.path.insert(0, {REF!r})
+sys.modules['webdataset'] = types.ModuleType('webdataset')
+import ae
+torch.manual_seed(123)
+m = ae.VAE(64, 3, 32, 3, [1, 2], 2, 4, False, True, False)
+torch.save(m.state_dict(), sys.argv[1])
+"""
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "ref_sd.pt")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, "PYTHONPATH": ""})
+        ref_sd = torch.load(path)
+    import ae
+
+    torch.manual_seed(123)
+    mine = ae.VAE(64, 3, 32, 3, [1, 2], 2, 4, False, True, False).state_dict()
+    assert set(mine) == set(ref_sd)
+    for k in ref_sd:
+        assert torch.equal(mine[k], ref_sd[k]), k

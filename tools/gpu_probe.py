@@ -357,6 +357,55 @@ def group_elem():
     return ok
 
 
+def group_lpips():
+    ok = True
+    torch.manual_seed(0)
+    # max-pool fwd / bwd (ReLU-gated, first-max tie rule)
+    for (N, H, W, Cc) in [(2, 16, 16, 64), (1, 8, 24, 128)]:
+        x = rnd(N, H, W, Cc).relu().to(torch.bfloat16)
+        x[0, 0:2, 0:2, :] = 1.0  # ties
+        y = torch.zeros(N, H // 2, W // 2, Cc, device=dev, dtype=torch.bfloat16)
+        native.check(L.vqb_maxpool2_fwd(native.ptr(x), native.ptr(y), N, H // 2, W // 2, Cc, native.stream_ptr()))
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        yr = F.max_pool2d(xr, 2)
+        torch.cuda.synchronize()
+        ok &= report(f"maxpool2 fwd {N}x{H}x{W}x{Cc}", y, yr.permute(0, 2, 3, 1), tol=1e-6)
+        dy = rnd(N, H // 2, W // 2, Cc).to(torch.bfloat16)
+        dx = torch.zeros_like(x)
+        native.check(L.vqb_maxpool2_bwd(native.ptr(x), native.ptr(dy), 0, native.ptr(dx), N, H // 2, W // 2, Cc, 1,
+                                        native.stream_ptr()))
+        torch.cuda.synchronize()
+        (gref,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
+        gref = gref * (xr > 0)
+        ok &= report("   bwd (relu gated)", dx, gref.permute(0, 2, 3, 1), tol=1e-6)
+    # LPIPS tail
+    for (N, H, W, Cc) in [(2, 16, 16, 64), (2, 8, 8, 128), (3, 4, 4, 256), (2, 4, 4, 512), (1, 32, 32, 64)]:
+        f0 = rnd(N, H, W, Cc).relu().to(torch.bfloat16)
+        f1 = rnd(N, H, W, Cc).relu().to(torch.bfloat16)
+        w = torch.rand(Cc, device=dev) / Cc
+        out = torch.zeros(N, device=dev)
+        native.check(L.vqb_lpips_tail_fwd(native.ptr(f0), native.ptr(f1), native.ptr(w), native.ptr(out), N, H * W, Cc,
+                                          native.stream_ptr()))
+        a = f0.float().permute(0, 3, 1, 2).requires_grad_(True)
+        b = f1.float().permute(0, 3, 1, 2)
+
+        def nrm(t_):
+            return t_ / (torch.sqrt(torch.sum(t_ ** 2, dim=1, keepdim=True)) + 1e-10)
+
+        ref = (F.conv2d((nrm(a) - nrm(b)) ** 2, w.view(1, Cc, 1, 1))).mean([2, 3]).reshape(N)
+        torch.cuda.synchronize()
+        ok &= report(f"lpips_tail fwd {N}x{H}x{W}x{Cc}", out[None], ref[None], tol=1e-4)
+        g = torch.rand(N, device=dev) + 0.5
+        df0 = torch.zeros_like(f0)
+        native.check(L.vqb_lpips_tail_bwd(native.ptr(f0), native.ptr(f1), native.ptr(w), native.ptr(g), native.ptr(df0),
+                                          N, H * W, Cc, native.stream_ptr()))
+        torch.cuda.synchronize()
+        (gref,) = torch.autograd.grad(ref, a, g)
+        gref = gref * (a > 0)
+        ok &= report("   bwd (relu gated)", df0, gref.permute(0, 2, 3, 1), tol=1e-2)
+    return ok
+
+
 def group_gemm():
     ok = True
     ok &= case_gemm(128, 64, 16)

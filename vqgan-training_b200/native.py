@@ -76,6 +76,10 @@ def load():
         "vqb_upsample2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vqb_colsum": (i32, [vp, vp, i64, i32, vp]),
         "vqb_wgrad_reduce": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+        "vqb_maxpool2_fwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "vqb_maxpool2_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "vqb_lpips_tail_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+        "vqb_lpips_tail_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name, None)

@@ -1,0 +1,399 @@
+"""torch.autograd.Functions over the native sm_100a kernels (libvqb200.so).
+
+Internal activation format: contiguous bf16 tensors of shape [N, H, W, Cp] (NHWC, Cp = channels padded to a multiple
+of 8, pad channels zero). Master weights / gradients stay fp32 OIHW nn.Parameters (the reference's state_dict
+contract); bf16 packed copies for the tensor-core kernels are caches keyed on the parameter version.
+
+Every op here launches hand-written CUDA; nothing falls back to ATen for the math.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+import native
+import plans
+from native import EPI_BIAS, EPI_MASK, EPI_RELU, EPI_RES, check, ptr, stream_ptr
+
+_tapmap_cache = {}
+
+
+def _L():
+    return native.load()
+
+
+def require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("vqgan-training_b200: the hot path runs on sm_100a CUDA tensors only (no CPU fallback)")
+
+
+def tapmap_tensor(tapmap, device) -> torch.Tensor:
+    key = (tuple(tapmap), str(device))
+    t = _tapmap_cache.get(key)
+    if t is None:
+        t = torch.tensor(list(tapmap), dtype=torch.int32, device=device)
+        _tapmap_cache[key] = t
+    return t
+
+
+def pack_weights(weight: torch.Tensor, tapmap, transpose: bool, Kpad: int) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [R][len(tapmap)][Kpad] (R = Cin if transpose else Cout)."""
+    Cout, Cin, KH, KW = weight.shape
+    R = Cin if transpose else Cout
+    out = torch.empty(R, len(tapmap), Kpad, device=weight.device, dtype=torch.bfloat16)
+    tm = tapmap_tensor(tapmap, weight.device)
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    check(_L().vqb_pack_weights(ptr(w), ptr(out), Cout, Cin, KH * KW, len(tapmap), ptr(tm), 1 if transpose else 0,
+                                Kpad, stream_ptr()), "pack_weights")
+    return out
+
+
+class PackedCache:
+    """bf16 packed copies of one fp32 OIHW parameter, refreshed when the parameter changes."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, weight: torch.Tensor, key, tapmap, transpose, Kpad):
+        ver = (weight._version, weight.data_ptr())
+        ent = self._store.get(key)
+        if ent is None or ent[0] != ver:
+            ent = (ver, pack_weights(weight, tapmap, transpose, Kpad))
+            self._store[key] = ent
+        return ent[1]
+
+
+def _wgrad_block_n(cols: int) -> int:
+    for c in (256, 192, 128, 64):
+        if cols % c == 0:
+            return c
+    return 64
+
+
+def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
+    cols = len(g.taps) * ((g.C + 63) // 64) * 64
+    tiles = ((Cout_pad + 127) // 128) * (cols // _wgrad_block_n(cols))
+
+    def p2(v, cap):
+        p = 1
+        while p < v:
+            p <<= 1
+        return min(p, cap)
+
+    bw = p2(g.Wo, 64)
+    bh = p2(g.Ho, 64 // bw)
+    bn = 64 // (bw * bh)
+    boxes = -(-g.Wo // bw) * -(-g.Ho // bh) * -(-g.N // bn)
+    want = -(-2 * 148 // tiles)
+    return max(1, min(want, max(1, boxes // 4)))
+
+
+def run_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: int, out: torch.Tensor, out_strides,
+                  out_ptr_offset_bytes=0, bias=None, res=None, mask=None, relu=False, out_f32=False):
+    flags = (EPI_BIAS if bias is not None else 0) | (EPI_RES if res is not None else 0) | \
+            (EPI_MASK if mask is not None else 0) | (EPI_RELU if relu else 0)
+    d = plans.conv_desc(g, Cout, out_strides, flags, out_f32)
+    off = out_ptr_offset_bytes
+    check(_L().vqb_conv_gemm(d, ptr(a), ptr(wp), ptr(bias), (ptr(res) + off) if res is not None else 0,
+                             (ptr(mask) + off) if mask is not None else 0, ptr(out) + off, 0, stream_ptr()),
+          "conv_gemm")
+
+
+def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape, Cout_pad: int) -> torch.Tensor:
+    """-> OIHW fp32 gradient for a conv whose forward geometry is g."""
+    Cout, Cin, KH, KW = weight_shape
+    ksplit = choose_ksplit(g, Cout_pad)
+    d = plans.wgrad_desc(g, Cout_pad, ksplit)
+    cols = _L().vqb_wgrad_cols(len(g.taps), g.C)
+    partial = torch.empty(ksplit, Cout_pad, cols, device=x.device, dtype=torch.float32)
+    check(_L().vqb_wgrad_gemm(d, ptr(dy), ptr(x), ptr(partial), stream_ptr()), "wgrad_gemm")
+    grad = torch.empty(Cout, Cin, KH, KW, device=x.device, dtype=torch.float32)
+    tm = tapmap_tensor(g.tapmap, x.device)
+    check(_L().vqb_wgrad_reduce(ptr(partial), ptr(grad), ksplit, Cout, Cout_pad, Cin, KH * KW, len(g.taps),
+                                cols // len(g.taps), ptr(tm), 0, stream_ptr()), "wgrad_reduce")
+    return grad
+
+
+def colsum(x2d_rows: int, x: torch.Tensor, C: int) -> torch.Tensor:
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    check(_L().vqb_colsum(ptr(x), ptr(out), x2d_rows, C, stream_ptr()), "colsum")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ToNHWC(torch.autograd.Function):
+    """[N,C,H,W] fp32 -> [N,H,W,Cp] bf16, optional per-channel (x - shift) * inv_scale (LPIPS ScalingLayer,
+    utils.py:70-71). Backward: NHWC bf16 grad -> NCHW fp32 (* inv_scale)."""
+
+    @staticmethod
+    def forward(ctx, x, shift, inv_scale):
+        require_cuda(x)
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        N, C, H, W = x.shape
+        Cp = plans.cpad(C)
+        y = torch.empty(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
+        check(_L().vqb_nchw_to_nhwc(ptr(x), ptr(y), N, C, H, W, Cp, ptr(shift), ptr(inv_scale), stream_ptr()),
+              "nchw_to_nhwc")
+        ctx.shape = (N, C, H, W, Cp)
+        ctx.inv_scale = inv_scale
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        N, C, H, W, Cp = ctx.shape
+        gy = gy.contiguous()
+        gx = torch.empty(N, C, H, W, device=gy.device, dtype=torch.float32)
+        check(_L().vqb_nhwc_to_nchw(ptr(gy), ptr(gx), N, C, H, W, Cp, ptr(ctx.inv_scale), stream_ptr()),
+              "nhwc_to_nchw")
+        return gx, None, None
+
+
+def to_nhwc(x, shift=None, inv_scale=None):
+    return ToNHWC.apply(x, shift, inv_scale)
+
+
+class ToNCHW(torch.autograd.Function):
+    """[N,H,W,Cp] bf16 -> [N,C,H,W] fp32 (module-boundary output when a caller wants the reference layout)."""
+
+    @staticmethod
+    def forward(ctx, y, C):
+        N, H, W, Cp = y.shape
+        y = y.contiguous()
+        x = torch.empty(N, C, H, W, device=y.device, dtype=torch.float32)
+        check(_L().vqb_nhwc_to_nchw(ptr(y), ptr(x), N, C, H, W, Cp, 0, stream_ptr()), "nhwc_to_nchw")
+        ctx.shape = (N, C, H, W, Cp)
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        N, C, H, W, Cp = ctx.shape
+        gx = gx.float().contiguous()
+        gy = torch.empty(N, H, W, Cp, device=gx.device, dtype=torch.bfloat16)
+        check(_L().vqb_nchw_to_nhwc(ptr(gx), ptr(gy), N, C, H, W, Cp, 0, 0, stream_ptr()), "nchw_to_nhwc")
+        return gy, None
+
+
+def to_nchw(y, C):
+    return ToNCHW.apply(y, C)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ConvFn(torch.autograd.Function):
+    """Convolution through the tcgen05 implicit-GEMM kernel.
+
+    kind: "s1" (k x k stride 1 same), "s2" (Downsample: pad (0,1,0,1) + 3x3 stride 2), "patch" (k x k stride k).
+    opts: relu (fused ReLU epilogue; the incoming gradient is then expected to be already gated by out > 0, which every
+    consumer of a ReLU output in this package does), input_is_relu (gate the data gradient by x > 0 in the dgrad
+    epilogue), nchw_out (write fp32 [N,Cout,H,W] directly: encoder z / decoder image)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, cache, kind, relu, input_is_relu, nchw_out):
+        require_cuda(x)
+        N, H, W, Cp = x.shape
+        Cout, Cin, KH, KW = weight.shape
+        assert Cp == plans.cpad(Cin), f"conv input has {Cp} channels, weight expects {Cin}"
+        x = x.contiguous()
+        if kind == "s1":
+            g = plans.geom_s1(N, H, W, Cp, KH)
+        elif kind == "s2":
+            g = plans.geom_s2(N, H, W, Cp)
+        elif kind == "patch":
+            g = plans.geom_patch(N, H, W, Cp, KH)
+        else:
+            raise ValueError(kind)
+        wp = cache.get(weight, ("fwd", kind), g.tapmap, False, Cp)
+        Cop = plans.cpad(Cout)
+        b = None
+        if bias is not None:
+            b = bias.detach()
+            if b.dtype != torch.float32:
+                b = b.float()
+        if nchw_out:
+            out = torch.empty(N, Cout, g.Ho, g.Wo, device=x.device, dtype=torch.float32)
+            run_conv_gemm(g, x, wp, Cout, out, plans.nchw_strides(Cout, g.Ho, g.Wo), bias=b, relu=relu, out_f32=True)
+        else:
+            alloc = torch.empty if Cop == Cout else torch.zeros
+            out = alloc(N, g.Ho, g.Wo, Cop, device=x.device, dtype=torch.bfloat16)
+            res = residual.contiguous() if residual is not None else None
+            run_conv_gemm(g, x, wp, Cout, out, plans.nhwc_strides(g.Ho, g.Wo, Cop), bias=b, res=res, relu=relu)
+        ctx.save_for_backward(x, weight)
+        ctx.cache, ctx.kind, ctx.g = cache, kind, g
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.input_is_relu, ctx.nchw_out = input_is_relu, nchw_out
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight = ctx.saved_tensors
+        g, kind, cache = ctx.g, ctx.kind, ctx.cache
+        N, H, W, Cp = x.shape
+        Cout, Cin, KH, KW = weight.shape
+        Cop = plans.cpad(Cout)
+        if ctx.nchw_out:
+            gn = gout.float().contiguous()
+            dy = torch.empty(N, g.Ho, g.Wo, Cop, device=x.device, dtype=torch.bfloat16)
+            check(_L().vqb_nchw_to_nhwc(ptr(gn), ptr(dy), N, Cout, g.Ho, g.Wo, Cop, 0, 0, stream_ptr()), "nchw_to_nhwc")
+        else:
+            dy = gout.contiguous()
+        gx = gw = gb = gres = None
+        if ctx.needs_input_grad[0]:
+            mask = x if ctx.input_is_relu else None
+            gx_alloc = torch.empty if Cp == Cin else torch.zeros
+            gx = gx_alloc(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
+            if kind == "s1":
+                gd = plans.geom_s1_dgrad(N, H, W, Cop, KH)
+                wpd = cache.get(weight, ("dgrad", kind), gd.tapmap, True, Cop)
+                run_conv_gemm(gd, dy, wpd, Cin, gx, plans.nhwc_strides(H, W, Cp), mask=mask)
+            elif kind == "s2":
+                for ph, pw, gd in plans.geom_s2_dgrad_classes(N, H, W, Cop):
+                    wpd = cache.get(weight, ("dgrad", kind, ph, pw), gd.tapmap, True, Cop)
+                    run_conv_gemm(gd, dy, wpd, Cin, gx, (H * W * Cp, 2 * W * Cp, 2 * Cp, 1),
+                                  out_ptr_offset_bytes=(ph * W + pw) * Cp * 2, mask=mask)
+            elif kind == "patch":
+                # non-overlapping windows: each input pixel belongs to exactly one (output pixel, tap): one 1-tap
+                # "conv" per tap writing the strided sub-grid of dx
+                k = KH
+                for kh in range(k):
+                    for kw in range(k):
+                        gd = plans.ConvGeom(N, g.Ho, g.Wo, Cop, [native.dense_view(N, g.Ho, g.Wo, Cop)], [(0, 0, 0)],
+                                            [kh * k + kw])
+                        wpd = cache.get(weight, ("dgrad", kind, kh, kw), gd.tapmap, True, Cop)
+                        run_conv_gemm(gd, dy, wpd, Cin, gx, (H * W * Cp, k * W * Cp, k * Cp, 1),
+                                      out_ptr_offset_bytes=(kh * W + kw) * Cp * 2, mask=mask)
+        if ctx.needs_input_grad[1]:
+            gw = run_wgrad(g, x, dy, weight.shape, Cop)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = colsum(N * g.Ho * g.Wo, dy, Cop)[:Cout]
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            gres = dy
+        return gx, gw, gb, gres, None, None, None, None, None
+
+
+def conv(x, weight, bias, cache, kind="s1", residual=None, relu=False, input_is_relu=False, nchw_out=False):
+    return ConvFn.apply(x, weight, bias, residual, cache, kind, relu, input_is_relu, nchw_out)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class GroupNormSiLUFn(torch.autograd.Function):
+    """FP32GroupNorm (32 groups, eps 1e-6, biased variance, fp32 statistics; ae.py:41-53) fused with swish
+    (ae.py:13-14): one statistics pass + one apply pass over bf16 NHWC, instead of cast/GN/cast/sigmoid/mul."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        require_cuda(x)
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty_like(x)
+        mr = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
+        ws = torch.empty(N * C * 2, device=x.device, dtype=torch.float64)
+        ga, be = gamma.detach().float(), beta.detach().float()
+        check(_L().vqb_gn_silu_fwd(ptr(x), ptr(y), ptr(ga), ptr(be), ptr(mr), ptr(ws), N, H * W, C, groups, eps,
+                                   1 if silu else 0, stream_ptr()), "gn_silu_fwd")
+        ctx.save_for_backward(x, gamma, beta, mr)
+        ctx.groups, ctx.silu = groups, silu
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, beta, mr = ctx.saved_tensors
+        N, H, W, C = x.shape
+        gy = gy.contiguous()
+        dx = torch.empty_like(x)
+        dg = torch.empty(C, device=x.device, dtype=torch.float32)
+        db = torch.empty(C, device=x.device, dtype=torch.float32)
+        ws = torch.empty(N * C * 2 + N * ctx.groups * 2, device=x.device, dtype=torch.float32)
+        ga, be = gamma.detach().float(), beta.detach().float()
+        check(_L().vqb_gn_silu_bwd(ptr(x), ptr(gy), 0, ptr(dx), ptr(ga), ptr(be), ptr(mr), ptr(dg), ptr(db), ptr(ws),
+                                   N, H * W, C, ctx.groups, 1 if ctx.silu else 0, stream_ptr()), "gn_silu_bwd")
+        return dx, dg, db, None, None, None
+
+
+def group_norm_silu(x, gamma, beta, groups=32, eps=1e-6, silu=True):
+    return GroupNormSiLUFn.apply(x, gamma, beta, groups, eps, silu)
+
+
+class Upsample2xFn(torch.autograd.Function):
+    """nearest x2 (ae.py:165); backward = 2x2 sum."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty(N, 2 * H, 2 * W, C, device=x.device, dtype=x.dtype)
+        check(_L().vqb_upsample2x_fwd(ptr(x), ptr(y), N, H, W, C, stream_ptr()), "upsample2x_fwd")
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = gy.contiguous()
+        N, H2, W2, C = gy.shape
+        gx = torch.empty(N, H2 // 2, W2 // 2, C, device=gy.device, dtype=gy.dtype)
+        check(_L().vqb_upsample2x_bwd(ptr(gy), ptr(gx), N, H2 // 2, W2 // 2, C, stream_ptr()), "upsample2x_bwd")
+        return gx
+
+
+def upsample2x(x):
+    return Upsample2xFn.apply(x)
+
+
+class MaxPool2Fn(torch.autograd.Function):
+    """2x2/2 max-pool of a post-ReLU activation. The backward routes dy to the first maximum of each window and gates
+    it by x > 0, i.e. it returns the gradient of the *pre-activation* of the conv that produced x."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty(N, H // 2, W // 2, C, device=x.device, dtype=x.dtype)
+        check(_L().vqb_maxpool2_fwd(ptr(x), ptr(y), N, H // 2, W // 2, C, stream_ptr()), "maxpool2_fwd")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, H, W, C = x.shape
+        gx = torch.empty_like(x)
+        check(_L().vqb_maxpool2_bwd(ptr(x), ptr(gy), 0, ptr(gx), N, H // 2, W // 2, C, 1, stream_ptr()),
+              "maxpool2_bwd")
+        return gx
+
+
+def maxpool2(x):
+    return MaxPool2Fn.apply(x)
+
+
+class LpipsTailFn(torch.autograd.Function):
+    """One LPIPS layer (utils.py:46-53,134-140): unit-normalise over channels, squared difference, 1x1 lin, spatial
+    mean -> [N]. Gradient only w.r.t. f0 (reconstruction branch), gated by f0 > 0 (post-ReLU feature)."""
+
+    @staticmethod
+    def forward(ctx, f0, f1, w):
+        f0, f1 = f0.contiguous(), f1.contiguous()
+        N, H, W, C = f0.shape
+        out = torch.zeros(N, device=f0.device, dtype=torch.float32)
+        wv = w.detach().reshape(-1).float().contiguous()
+        check(_L().vqb_lpips_tail_fwd(ptr(f0), ptr(f1), ptr(wv), ptr(out), N, H * W, C, stream_ptr()), "lpips_tail_fwd")
+        ctx.save_for_backward(f0, f1, wv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f0, f1, wv = ctx.saved_tensors
+        N, H, W, C = f0.shape
+        g = g.float().contiguous()
+        df0 = torch.empty_like(f0)
+        check(_L().vqb_lpips_tail_bwd(ptr(f0), ptr(f1), ptr(wv), ptr(g), ptr(df0), N, H * W, C, stream_ptr()),
+              "lpips_tail_bwd")
+        return df0, None, None
+
+
+def lpips_tail(f0, f1, w):
+    return LpipsTailFn.apply(f0, f1, w)
