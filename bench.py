@@ -99,6 +99,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def cpu_threads():
+    """Threads for the CPU arm: every core up to 32 (batch-1 convolutions of this size stop scaling — and with 100+
+    threads get slower — beyond that; measured 0.007 img/s at 128 threads vs 0.12 img/s at 8 on the survey box)."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("VQB_CPU_THREADS", "32"))))
+
+
 def cpu_step_runner(batch=1, threads=None):
     """The reference arithmetic on host cores: oracle restatement (fp32, torch CPU) of one training step incl. AdamW."""
     from oracle import lpips_oracle as LP
@@ -143,11 +149,12 @@ def run_reference(args, rank, world):
     the GPU box) on this box's host cores, same metric/unit/config. Rank 0 only."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     step, b = cpu_step_runner(batch=1, threads=threads)
-    for _ in range(max(0, min(args.warmup, 1))):
-        step()
-    k = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    step()  # warm-up (also tells us how long one step takes on this host)
+    first = time.perf_counter() - t0
+    k = max(1, min(args.steps, 3 if first < 20 else 1))
     t0 = time.perf_counter()
     for _ in range(k):
         step()
@@ -321,11 +328,13 @@ def main():
                                "ms_per_step": prof["wgrad"]["ms"]},
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = cpu_threads()
             step, b = cpu_step_runner(batch=1, threads=threads)
-            step()
             t0 = time.perf_counter()
-            n = 2
+            step()
+            first = time.perf_counter() - t0
+            n = 2 if first < 15 else 1
+            t0 = time.perf_counter()
             for _ in range(n):
                 step()
             dt = (time.perf_counter() - t0) / n

@@ -9,6 +9,8 @@ namespace vqb {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_launches{0};
+static std::atomic<int> g_debug{0};
+int debug_mode() { return g_debug.load(std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -110,5 +112,6 @@ const char* vqb_last_error(void) { return vqb::g_err; }
 int vqb_version(void) { return 100; }
 int vqb_device_ok(void) { return (vqb::device_is_sm100() && vqb::get_encode_fn() != nullptr) ? 1 : 0; }
 int vqb_kernel_launch_count(void) { return vqb::g_launches.load(std::memory_order_relaxed); }
+int vqb_set_debug_mode(int m) { vqb::g_debug.store(m); return 0; }
 
 }  // extern "C"

@@ -37,6 +37,7 @@ struct alignas(64) ConvParams {
     int32_t n_tiles, total_tiles;
     int32_t block_n, stages, tmem_cols;
     int32_t flags, out_f32;
+    int32_t dbg, _pad0;
     int64_t on, oh, ow, oc;
     void* out;
     const void* res;
@@ -94,19 +95,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
-        uint32_t stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        uint32_t stage = 0, phase = 0, tile_iter = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
             const int n_tile = tile % p.n_tiles;
             const int m_tile = tile / p.n_tiles;
             const int tw = m_tile % p.tiles_w;
             const int th = (m_tile / p.tiles_w) % p.tiles_h;
             const int tn = m_tile / (p.tiles_w * p.tiles_h);
             const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
-            for (int t = 0; t < p.ntaps; ++t) {
+            // K-blocks are walked in a per-CTA rotated order: persistent CTAs run in lock-step, and without the
+            // rotation all 148 of them request the SAME weight rows (and neighbouring activation rows) from the same
+            // L2 slices at the same time (measured: TMA-only throughput 2-3x lower on the small-weight layers).
+            const int rot = (p.dbg & 4) ? 0 : static_cast<int>((blockIdx.x * 5u + tile_iter * 3u) % static_cast<uint32_t>(num_kb));
+            for (int kbi = 0; kbi < num_kb; ++kbi) {
+                int kb = kbi + rot;
+                if (kb >= num_kb) kb -= num_kb;
+                const int t = kb / p.kchunks;
+                const int kc = kb - t * p.kchunks;
                 const CUtensorMap* am = &p.amap[p.tap_view[t]];
                 const int cw = w0 + p.tap_dw[t], chh = h0 + p.tap_dh[t];
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                {
                     mbar_wait(&empty[stage], phase ^ 1);
+                    if ((p.dbg & 3) == 1) {
+                        mbar_arrive(&full[stage]);
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
                     tma_load_4d(am, &full[stage], sA + stage * kABytes, kc * kBlockK, cw, chh, n0);
                     tma_load_2d(&p.bmap, &full[stage], sB + stage * b_bytes, t * p.C + kc * kBlockK,
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, 2);
                     const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, 2);
-                    umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if ((p.dbg & 3) != 2) umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
                 if (++stage == stages) {
@@ -352,6 +369,7 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
     p.mask = mask;
     p.bias = bias;
     p.stats = stats;
+    p.dbg = debug_mode();
     for (int t = 0; t < d->ntaps; ++t) {
         p.tap_view[t] = d->taps[t].view;
         p.tap_dw[t] = d->taps[t].dw;

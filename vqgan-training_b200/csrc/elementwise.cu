@@ -16,6 +16,11 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void cvt8(const uint4& u, float (&f)[8]) {
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
     uint4 u;
     u.x = pack_bf16x2(f[0], f[1]);
@@ -111,7 +116,23 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __r
     const int p1 = min(HW, p0 + pix_per_chunk);
     if (pr < R) {
         const __nv_bfloat16* xb = x + (static_cast<int64_t>(n) * HW) * C + cv * 8;
-        for (int p = p0 + pr; p < p1; p += R) {
+        int p = p0 + pr;
+        for (; p + 3 * R < p1; p += 4 * R) {  // 4 independent 16-byte loads in flight per thread
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = ldg16(xb + static_cast<int64_t>(p + k * R) * C);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f[8];
+                cvt8(u[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s[j] += f[j];
+                    q[j] += f[j] * f[j];
+                }
+            }
+        }
+        for (; p < p1; p += R) {
             float f[8];
             load8(xb + static_cast<int64_t>(p) * C, f);
 #pragma unroll
@@ -168,7 +189,24 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
     const int p0 = blockIdx.x * pix_per_chunk;
     const int p1 = min(HW, p0 + pix_per_chunk);
     const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
-    for (int p = p0 + pr; p < p1; p += R) {
+    int p = p0 + pr;
+    for (; p + 3 * R < p1; p += 4 * R) {
+        uint4 u4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u4[k] = ldg16(x + base + static_cast<int64_t>(p + k * R) * C);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[8];
+            cvt8(u4[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float u = fmaf(a[j], f[j], b[j]);
+                f[j] = silu ? u * sigmoidf_(u) : u;
+            }
+            store8(y + base + static_cast<int64_t>(p + k * R) * C, f);
+        }
+    }
+    for (; p < p1; p += R) {
         float f[8];
         load8(x + base + static_cast<int64_t>(p) * C, f);
 #pragma unroll
@@ -206,10 +244,18 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const 
         const int p0 = blockIdx.x * pix_per_chunk;
         const int p1 = min(HW, p0 + pix_per_chunk);
         const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
-        for (int p = p0 + pr; p < p1; p += R) {
+        for (int p = p0 + pr; p < p1; p += 2 * R) {
+            const bool two = (p + R) < p1;
+            uint4 ux0 = ldg16(x + base + static_cast<int64_t>(p) * C);
+            uint4 ud0 = ldg16(dy + base + static_cast<int64_t>(p) * C);
+            uint4 ux1 = two ? ldg16(x + base + static_cast<int64_t>(p + R) * C) : make_uint4(0, 0, 0, 0);
+            uint4 ud1 = two ? ldg16(dy + base + static_cast<int64_t>(p + R) * C) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+            if (k == 1 && !two) break;
             float f[8], d[8];
-            load8(x + base + static_cast<int64_t>(p) * C, f);
-            load8(dy + base + static_cast<int64_t>(p) * C, d);
+            cvt8(k ? ux1 : ux0, f);
+            cvt8(k ? ud1 : ud0, d);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float xh = (f[j] - mean[j]) * rstd[j];
@@ -221,6 +267,7 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const 
                 }
                 s1[j] += du;
                 s2[j] += du * xh;
+            }
             }
         }
 #pragma unroll
@@ -285,12 +332,22 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
     const int p0 = blockIdx.x * pix_per_chunk;
     const int p1 = min(HW, p0 + pix_per_chunk);
     const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
-    for (int p = p0 + pr; p < p1; p += R) {
+    for (int pp = p0 + pr; pp < p1; pp += 2 * R) {
+        const bool two = (pp + R) < p1;
+        const int64_t off0 = base + static_cast<int64_t>(pp) * C, off1 = off0 + static_cast<int64_t>(R) * C;
+        uint4 ux0 = ldg16(x + off0), ud0 = ldg16(dy + off0);
+        uint4 ua0 = add ? ldg16(add + off0) : make_uint4(0, 0, 0, 0);
+        uint4 ux1 = two ? ldg16(x + off1) : make_uint4(0, 0, 0, 0);
+        uint4 ud1 = two ? ldg16(dy + off1) : make_uint4(0, 0, 0, 0);
+        uint4 ua1 = (two && add) ? ldg16(add + off1) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !two) break;
         float f[8], d[8], r[8];
-        const int64_t off = base + static_cast<int64_t>(p) * C;
-        load8(x + off, f);
-        load8(dy + off, d);
-        if (add) load8(add + off, r);
+        const int64_t off = k ? off1 : off0;
+        cvt8(k ? ux1 : ux0, f);
+        cvt8(k ? ud1 : ud0, d);
+        cvt8(k ? ua1 : ua0, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float xh = (f[j] - mean[j]) * rstd[j];
@@ -305,6 +362,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
             f[j] = v;
         }
         store8(dx + off, f);
+        }
     }
 }
 
@@ -367,7 +425,20 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
         for (int j = 0; j < 8; ++j) s[j] = 0.f;
         const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_chunk;
         const int64_t p1 = min(P, p0 + pix_per_chunk);
-        for (int64_t p = p0 + pr; p < p1; p += R) {
+        int64_t p = p0 + pr;
+        for (; p + 3 * R < p1; p += 4 * R) {
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = ldg16(x + (p + k * R) * C + cv * 8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f[8];
+                cvt8(u[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += f[j];
+            }
+        }
+        for (; p < p1; p += R) {
             float f[8];
             load8(x + p * C + cv * 8, f);
 #pragma unroll

@@ -53,10 +53,19 @@ def pack_weights(weight: torch.Tensor, tapmap, transpose: bool, Kpad: int) -> to
 
 
 class PackedCache:
-    """bf16 packed copies of one fp32 OIHW parameter, refreshed when the parameter changes."""
+    """Per-conv-layer caches: bf16 packed copies of the fp32 OIHW parameter (refreshed when the parameter changes) and
+    the shape-dependent geometry objects / C descriptors (built once per input shape)."""
 
     def __init__(self):
         self._store = {}
+        self._geoms = {}
+
+    def geom(self, key, builder):
+        g = self._geoms.get(key)
+        if g is None:
+            g = builder()
+            self._geoms[key] = g
+        return g
 
     def get(self, weight: torch.Tensor, key, tapmap, transpose, Kpad):
         ver = (weight._version, weight.data_ptr())
@@ -84,19 +93,24 @@ def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
             p <<= 1
         return min(p, cap)
 
-    bw = p2(g.Wo, 64)
-    bh = p2(g.Ho, 64 // bw)
-    bn = 64 // (bw * bh)
+    bw = p2(g.Wo, 128)  # the kernel walks K in boxes of 128 pixels
+    bh = p2(g.Ho, 128 // bw)
+    bn = 128 // (bw * bh)
     boxes = -(-g.Wo // bw) * -(-g.Ho // bh) * -(-g.N // bn)
     want = -(-2 * 148 // tiles)
-    return max(1, min(want, max(1, boxes // 4)))
+    return max(1, min(want, max(1, boxes // 2)))
 
 
 def run_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: int, out: torch.Tensor, out_strides,
                   out_ptr_offset_bytes=0, bias=None, res=None, mask=None, relu=False, out_f32=False):
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_RES if res is not None else 0) | \
             (EPI_MASK if mask is not None else 0) | (EPI_RELU if relu else 0)
-    d = plans.conv_desc(g, Cout, out_strides, flags, out_f32)
+    dk = (Cout, tuple(out_strides), flags, out_f32)
+    descs = g.__dict__.setdefault("_descs", {})
+    d = descs.get(dk)
+    if d is None:
+        d = plans.conv_desc(g, Cout, out_strides, flags, out_f32)
+        descs[dk] = d
     off = out_ptr_offset_bytes
     check(_L().vqb_conv_gemm(d, ptr(a), ptr(wp), ptr(bias), (ptr(res) + off) if res is not None else 0,
                              (ptr(mask) + off) if mask is not None else 0, ptr(out) + off, 0, stream_ptr()),
@@ -106,9 +120,14 @@ def run_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: in
 def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape, Cout_pad: int) -> torch.Tensor:
     """-> OIHW fp32 gradient for a conv whose forward geometry is g."""
     Cout, Cin, KH, KW = weight_shape
-    ksplit = choose_ksplit(g, Cout_pad)
-    d = plans.wgrad_desc(g, Cout_pad, ksplit)
-    cols = _L().vqb_wgrad_cols(len(g.taps), g.C)
+    wk = ("wgrad", Cout_pad)
+    descs = g.__dict__.setdefault("_descs", {})
+    ent = descs.get(wk)
+    if ent is None:
+        ksplit = choose_ksplit(g, Cout_pad)
+        ent = (ksplit, plans.wgrad_desc(g, Cout_pad, ksplit), _L().vqb_wgrad_cols(len(g.taps), g.C))
+        descs[wk] = ent
+    ksplit, d, cols = ent
     partial = torch.empty(ksplit, Cout_pad, cols, device=x.device, dtype=torch.float32)
     check(_L().vqb_wgrad_gemm(d, ptr(dy), ptr(x), ptr(partial), stream_ptr()), "wgrad_gemm")
     grad = torch.empty(Cout, Cin, KH, KW, device=x.device, dtype=torch.float32)
@@ -200,11 +219,11 @@ class ConvFn(torch.autograd.Function):
         assert Cp == plans.cpad(Cin), f"conv input has {Cp} channels, weight expects {Cin}"
         x = x.contiguous()
         if kind == "s1":
-            g = plans.geom_s1(N, H, W, Cp, KH)
+            g = cache.geom(("f", N, H, W), lambda: plans.geom_s1(N, H, W, Cp, KH))
         elif kind == "s2":
-            g = plans.geom_s2(N, H, W, Cp)
+            g = cache.geom(("f", N, H, W), lambda: plans.geom_s2(N, H, W, Cp))
         elif kind == "patch":
-            g = plans.geom_patch(N, H, W, Cp, KH)
+            g = cache.geom(("f", N, H, W), lambda: plans.geom_patch(N, H, W, Cp, KH))
         else:
             raise ValueError(kind)
         wp = cache.get(weight, ("fwd", kind), g.tapmap, False, Cp)
@@ -247,11 +266,11 @@ class ConvFn(torch.autograd.Function):
             gx_alloc = torch.empty if Cp == Cin else torch.zeros
             gx = gx_alloc(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
             if kind == "s1":
-                gd = plans.geom_s1_dgrad(N, H, W, Cop, KH)
+                gd = cache.geom(("d", N, H, W), lambda: plans.geom_s1_dgrad(N, H, W, Cop, KH))
                 wpd = cache.get(weight, ("dgrad", kind), gd.tapmap, True, Cop)
                 run_conv_gemm(gd, dy, wpd, Cin, gx, plans.nhwc_strides(H, W, Cp), mask=mask)
             elif kind == "s2":
-                for ph, pw, gd in plans.geom_s2_dgrad_classes(N, H, W, Cop):
+                for ph, pw, gd in cache.geom(("d", N, H, W), lambda: plans.geom_s2_dgrad_classes(N, H, W, Cop)):
                     wpd = cache.get(weight, ("dgrad", kind, ph, pw), gd.tapmap, True, Cop)
                     run_conv_gemm(gd, dy, wpd, Cin, gx, (H * W * Cp, 2 * W * Cp, 2 * Cp, 1),
                                   out_ptr_offset_bytes=(ph * W + pw) * Cp * 2, mask=mask)
@@ -261,8 +280,8 @@ class ConvFn(torch.autograd.Function):
                 k = KH
                 for kh in range(k):
                     for kw in range(k):
-                        gd = plans.ConvGeom(N, g.Ho, g.Wo, Cop, [native.dense_view(N, g.Ho, g.Wo, Cop)], [(0, 0, 0)],
-                                            [kh * k + kw])
+                        gd = cache.geom(("d", N, H, W, kh, kw), lambda: plans.ConvGeom(
+                            N, g.Ho, g.Wo, Cop, [native.dense_view(N, g.Ho, g.Wo, Cop)], [(0, 0, 0)], [kh * k + kw]))
                         wpd = cache.get(weight, ("dgrad", kind, kh, kw), gd.tapmap, True, Cop)
                         run_conv_gemm(gd, dy, wpd, Cin, gx, (H * W * Cp, k * W * Cp, k * Cp, 1),
                                       out_ptr_offset_bytes=(kh * W + kw) * Cp * 2, mask=mask)
