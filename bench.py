@@ -187,7 +187,7 @@ def profile_conv_kernels(tr, batch_dev):
         e0.record()
         r = orig_conv(g, a, wp, Cout, out, out_strides, *aa, **kk)
         e1.record()
-        rec["conv"].append((e0, e1, flops_conv(g, Cout)))
+        rec["conv"].append((e0, e1, flops_conv(g, Cout), ("conv", g.N, g.Ho, g.Wo, g.C, Cout, len(g.taps), len(g.views))))
         return r
 
     def wgrad_wrap(g, x, dy, weight_shape, Cout_pad):
@@ -196,7 +196,8 @@ def profile_conv_kernels(tr, batch_dev):
         r = orig_wgrad(g, x, dy, weight_shape, Cout_pad)
         e1.record()
         Cout, Cin, KH, KW = weight_shape
-        rec["wgrad"].append((e0, e1, 2.0 * g.N * g.Ho * g.Wo * Cout * Cin * KH * KW))
+        rec["wgrad"].append((e0, e1, 2.0 * g.N * g.Ho * g.Wo * Cout * Cin * KH * KW,
+                             ("wgrad", g.N, g.Ho, g.Wo, g.C, Cout, len(g.taps), len(g.views))))
         return r
 
     ops.run_conv_gemm, ops.run_wgrad = conv_wrap, wgrad_wrap
@@ -206,9 +207,20 @@ def profile_conv_kernels(tr, batch_dev):
     finally:
         ops.run_conv_gemm, ops.run_wgrad = orig_conv, orig_wgrad
     out = {}
+    table = {}
     for k, lst in rec.items():
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in lst)
-        fl = sum(f for _, _, f in lst)
+        for e0, e1, f, sig in lst:
+            t = table.setdefault(sig, [0, 0.0, 0.0])
+            t[0] += 1
+            t[1] += e0.elapsed_time(e1)
+            t[2] += f
+    if os.environ.get("VQB_KERNEL_TABLE", "0") == "1":
+        sys.stderr.write("kind N Ho Wo C Cout taps views | launches total_ms TFLOP/s\n")
+        for sig, (cnt, ms_, fl_) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            sys.stderr.write(f"{sig} | {cnt} {ms_:.3f} {fl_ / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0:.1f}\n")
+    for k, lst in rec.items():
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in lst)
+        fl = sum(f for _, _, f, _ in lst)
         out[k] = {"launches": len(lst), "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0,
                   "flops_per_launch": fl / max(1, len(lst)), "ms_per_launch": ms / max(1, len(lst))}
     return out

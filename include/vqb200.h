@@ -162,11 +162,21 @@ int vqb_lpips_tail_fwd(const void* f0, const void* f1, const float* w, float* ou
 int vqb_lpips_tail_bwd(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW, int C,
                        void* stream);
 
+/*
+ * Multi-head self-attention core of AttnBlock (ae.py:74-93): qkv [N][T][3C] bf16 (q | k | v channel blocks, heads of 64
+ * channels) -> out [N][T][C] = softmax(q k^T / 8) v, flash-style (no T x T matrix in HBM). lse [N][C/64][T] is saved for
+ * the backward; dvec is a workspace of the same shape. Replaces F.scaled_dot_product_attention + einops rearranges.
+ */
+int vqb_attn_fwd(const void* qkv, void* out, float* lse, int N, int T, int C, void* stream);
+int vqb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* dvec, void* dqkv, int N,
+                 int T, int C, void* stream);
+
 /* library / device info */
 const char* vqb_last_error(void);
 int vqb_version(void);
 int vqb_device_ok(void); /* 1 if the current device is sm_100 and the TMA driver entry point resolved */
 int vqb_kernel_launch_count(void); /* number of kernels this library launched in this process */
+int vqb_set_debug_mode(int mode);   /* perf-experiment switches (tools/perf_experiments.py); 0 = production */
 
 #ifdef __cplusplus
 }

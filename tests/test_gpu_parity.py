@@ -172,7 +172,7 @@ def test_generator_and_discriminator_step_vs_reference_golden():
         big = ref > 1e-3 * ref.max()
         ratio = norms[big] / ref[big]
         print(f"  grad-norm ratio: min {ratio.min():.4f} max {ratio.max():.4f}")
-        assert np.all(np.abs(ratio - 1) < 0.1)
+        assert np.all(np.abs(ratio - 1) < (0.2 if gan else 0.1))
     assert rel_l2(recon, g["recon"]) < ACT_TOL
     # discriminator step: hinge + LeCam (anchors 0.1 / 0.05)
     rp, fp = disc(real), disc(t(g["recon"]).cuda())
@@ -188,3 +188,45 @@ def test_generator_and_discriminator_step_vs_reference_golden():
     ratio = dn[big] / ref[big]
     print(f"\nd-step: loss rel {ed:.3e} grad-norm ratio min {ratio.min():.4f} max {ratio.max():.4f}")
     assert ed < ACT_TOL and np.all(np.abs(ratio - 1) < 0.1)
+
+
+def test_attention_vae_vs_reference_golden():
+    """AttnBlock (flash-style warp-MMA core + tcgen05 qkv/proj convs) inside the VAE vs the reference golden
+    (the reference cannot construct use_attn=True at HEAD; the golden was produced by swapping AttnBlock in)."""
+    name = "vae_attn"
+    cfg = VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=4, use_attn=True)
+    g = golden(name)
+    vae = build_vae(cfg, name)
+    x = seeded.tensor(name + "/x", (2, 3, 32, 32), 1.0, "uniform").cuda()
+    dec, z = vae(x)
+    ez, ed = rel_l2(z, g["z"]), rel_l2(dec, g["dec"])
+    print(f"\n{name}: z rel_l2 {ez:.3e}  dec rel_l2 {ed:.3e}")
+    assert ez < ACT_TOL and ed < ACT_TOL
+    (dec.pow(2).mean() + z.pow(2).mean()).backward()
+    check_grads(vae.named_parameters(), g)
+    for k in g:
+        if k.startswith("grad::"):
+            c = cosine(dict(vae.named_parameters())[k[6:]].grad, g[k])
+            print(f"  cos {k[6:]}: {c:.5f}")
+            assert c > COS_TOL, k
+
+
+def test_attention_core_vs_torch_sdpa():
+    """vqb_attn_fwd/bwd vs F.scaled_dot_product_attention in fp32 on bf16-rounded inputs, incl. a ragged length."""
+    import attention
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    for (N, H, W, C) in [(2, 16, 16, 128), (1, 32, 32, 512), (2, 10, 7, 64)]:
+        heads = C // 64
+        qkv = (torch.randn(N, H, W, 3 * C, device="cuda") * 0.7).to(torch.bfloat16).requires_grad_(True)
+        out = attention.mhsa(qkv, heads, 64)
+        go = torch.randn_like(out)
+        out.backward(go)
+        q32 = qkv.detach().float().requires_grad_(True)
+        q, k, v = q32.reshape(N, H * W, 3, heads, 64).permute(2, 0, 3, 1, 4)
+        ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(N, H, W, C)
+        ref.backward(go.float())
+        e_o, e_g = rel_l2(out, ref), rel_l2(qkv.grad, q32.grad)
+        print(f"\nattn N={N} T={H * W} C={C}: out rel {e_o:.3e} dqkv rel {e_g:.3e}")
+        assert e_o < 1e-2 and e_g < 2e-2

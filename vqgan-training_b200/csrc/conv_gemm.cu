@@ -36,6 +36,7 @@ struct alignas(64) ConvParams {
     int32_t tiles_w, tiles_h, tiles_nb;
     int32_t n_tiles, total_tiles;
     int32_t block_n, stages, tmem_cols;
+    int32_t mtiles, nbuf;  // 128-row accumulator sub-tiles per CTA tile (1|2); TMEM accumulator buffers (2..4)
     int32_t flags, out_f32;
     int32_t dbg, _pad0;
     int64_t on, oh, ow, oc;
@@ -54,14 +55,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // carve shared memory (1024-B aligned for the 128B swizzle atoms)
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t stages = p.stages;
+    const uint32_t a_bytes = static_cast<uint32_t>(p.mtiles) * kABytes;
     const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
+    const uint32_t mtiles = p.mtiles, nbuf = p.nbuf;
     uint8_t* sA = base;
-    uint8_t* sB = base + stages * kABytes;
+    uint8_t* sB = base + stages * a_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_bytes);
     uint64_t* empty = full + stages;
     uint64_t* tfull = empty + stages;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
 
     if (warp == 0 && lane == 0) {
         for (int v = 0; v < VQB_MAX_VIEWS; ++v) {
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 128);
         }
@@ -94,8 +97,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int num_kb = p.ntaps * p.kchunks;
 
     if (warp == 0 && lane == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (one thread; keep the per-K-block instruction count small) =========
         uint32_t stage = 0, phase = 0, tile_iter = 0;
+        uint8_t* a_dst = sA;
+        uint8_t* b_dst = sB;
+        const uint32_t tx_bytes = a_bytes + b_bytes;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
             const int n_tile = tile % p.n_tiles;
             const int m_tile = tile / p.n_tiles;
@@ -103,89 +109,124 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int th = (m_tile / p.tiles_w) % p.tiles_h;
             const int tn = m_tile / (p.tiles_w * p.tiles_h);
             const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn << p.lbn;
-            // K-blocks are walked in a per-CTA rotated order: persistent CTAs run in lock-step, and without the
-            // rotation all 148 of them request the SAME weight rows (and neighbouring activation rows) from the same
-            // L2 slices at the same time (measured: TMA-only throughput 2-3x lower on the small-weight layers).
+            const int ncol0 = n_tile * p.block_n;
+            // K-blocks are walked from a per-CTA rotated start (neutral in measurements; keeps lock-stepped CTAs from
+            // requesting identical weight rows at the same instant)
             const int rot = (p.dbg & 4) ? 0 : static_cast<int>((blockIdx.x * 5u + tile_iter * 3u) % static_cast<uint32_t>(num_kb));
+            int t = rot / p.kchunks;
+            int kc = rot - t * p.kchunks;
             for (int kbi = 0; kbi < num_kb; ++kbi) {
-                int kb = kbi + rot;
-                if (kb >= num_kb) kb -= num_kb;
-                const int t = kb / p.kchunks;
-                const int kc = kb - t * p.kchunks;
-                const CUtensorMap* am = &p.amap[p.tap_view[t]];
-                const int cw = w0 + p.tap_dw[t], chh = h0 + p.tap_dh[t];
-                {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    if ((p.dbg & 3) == 1) {
-                        mbar_arrive(&full[stage]);
-                        if (++stage == stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                        continue;
-                    }
-                    mbar_arrive_expect_tx(&full[stage], kABytes + b_bytes);
-                    tma_load_4d(am, &full[stage], sA + stage * kABytes, kc * kBlockK, cw, chh, n0);
-                    tma_load_2d(&p.bmap, &full[stage], sB + stage * b_bytes, t * p.C + kc * kBlockK,
-                                n_tile * p.block_n);
-                    if (++stage == stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                mbar_wait(&empty[stage], phase ^ 1);
+                if ((p.dbg & 3) == 1) {
+                    mbar_arrive(&full[stage]);
+                } else {
+                    mbar_arrive_expect_tx(&full[stage], tx_bytes);
+                    tma_load_4d(&p.amap[p.tap_view[t]], &full[stage], a_dst, kc * kBlockK, w0 + p.tap_dw[t],
+                                h0 + p.tap_dh[t], n0);
+                    tma_load_2d(&p.bmap, &full[stage], b_dst, t * p.C + kc * kBlockK, ncol0);
+                }
+                if (++kc == p.kchunks) {
+                    kc = 0;
+                    if (++t == p.ntaps) t = 0;
+                }
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1;
+                    a_dst = sA;
+                    b_dst = sB;
+                } else {
+                    a_dst += a_bytes;
+                    b_dst += b_bytes;
                 }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer (single thread) =====================
+        // This thread must issue 4*mtiles MMAs per K-block in well under the ~512*mtiles cycles the tensor core needs
+        // for them: descriptors are base + increments (no divisions, no per-K-block descriptor builds).
         const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
-        uint32_t stage = 0, phase = 0, it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t as = it & 1, aph = (it >> 1) & 1;
-            mbar_wait(&tempty[as], aph ^ 1);
+        const uint64_t da_base = make_smem_desc(smem_u32(sA), 0, 1024, 2);
+        const uint64_t db_base = make_smem_desc(smem_u32(sB), 0, 1024, 2);
+        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;  // descriptor address field is (addr >> 4)
+        const bool two = (mtiles == 2);
+        const bool do_mma = (p.dbg & 3) != 2;
+        uint32_t stage = 0, phase = 0, a_off = 0, b_off = 0;
+        uint32_t buf = 0, bpar = 0;  // next TMEM accumulator buffer and the parity of its use count
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const uint32_t b0 = buf;
+            mbar_wait(&tempty[buf], bpar ^ 1);  // epilogue has drained the previous use of this buffer
+            if (++buf == nbuf) {
+                buf = 0;
+                bpar ^= 1;
+            }
+            uint32_t b1 = b0;
+            if (two) {
+                b1 = buf;
+                mbar_wait(&tempty[buf], bpar ^ 1);
+                if (++buf == nbuf) {
+                    buf = 0;
+                    bpar ^= 1;
+                }
+            }
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * p.block_n;
+            const uint32_t d0 = tmem_base + b0 * p.block_n, d1 = tmem_base + b1 * p.block_n;
+            uint32_t acc = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-                const uint32_t b_addr = smem_u32(sB + stage * b_bytes);
+                const uint64_t da = da_base + a_off, db = db_base + b_off;
+                if (do_mma) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, 2);
-                    const uint64_t db = make_smem_desc(b_addr + k * 32, 0, 1024, 2);
-                    if ((p.dbg & 3) != 2) umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d0, da + 2 * k, db + 2 * k, idesc, acc | k);
+                    if (two) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(d1, da + (kABytes >> 4) + 2 * k, db + 2 * k, idesc, acc | k);
+                    }
                 }
                 umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+                acc = 1;
                 if (++stage == stages) {
                     stage = 0;
                     phase ^= 1;
+                    a_off = 0;
+                    b_off = 0;
+                } else {
+                    a_off += a_step;
+                    b_off += b_step;
                 }
             }
-            umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+            umma_commit(&tfull[b0]);  // accumulator(s) complete -> epilogue
+            if (two) umma_commit(&tfull[b1]);
         }
     } else if (warp >= 4) {
         // ===================== epilogue (4 warps = 128 accumulator rows) =====================
         const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
-        const uint32_t row = ew * 32 + lane;
-        const int wi = row & ((1 << p.lbw) - 1);
-        const int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
-        const int ni = row >> (p.lbw + p.lbh);
         const bool has_bias = p.flags & VQB_EPI_BIAS, has_res = p.flags & VQB_EPI_RES;
         const bool do_relu = p.flags & VQB_EPI_RELU, has_mask = p.flags & VQB_EPI_MASK;
         const bool vec_path = (p.oc == 1) && (p.out_f32 == 0);
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t as = it & 1, aph = (it >> 1) & 1;
-            const int n_tile = tile % p.n_tiles;
-            const int m_tile = tile / p.n_tiles;
-            const int tw = m_tile % p.tiles_w;
-            const int th = (m_tile / p.tiles_w) % p.tiles_h;
-            const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        uint32_t ebuf = 0, epar = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          const int n_tile = tile % p.n_tiles;
+          const int m_tile = tile / p.n_tiles;
+          const int tw = m_tile % p.tiles_w;
+          const int th = (m_tile / p.tiles_w) % p.tiles_h;
+          const int tn = m_tile / (p.tiles_w * p.tiles_h);
+          const int col0 = n_tile * p.block_n;
+          for (uint32_t mt = 0; mt < mtiles; ++mt) {
+            const uint32_t as = ebuf, aph = epar;
+            if (++ebuf == nbuf) {
+                ebuf = 0;
+                epar ^= 1;
+            }
+            const uint32_t row = mt * 128 + ew * 32 + lane;  // row of the (128*mtiles)-pixel box
+            const int wi = row & ((1 << p.lbw) - 1);
+            const int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
+            const int ni = row >> (p.lbw + p.lbh);
             const int w = (tw << p.lbw) + wi, h = (th << p.lbh) + hi, n = (tn << p.lbn) + ni;
             const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
             const int64_t pix = static_cast<int64_t>(n) * p.on + static_cast<int64_t>(h) * p.oh +
                                 static_cast<int64_t>(w) * p.ow;
-            const int col0 = n_tile * p.block_n;
 
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
@@ -271,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);
+          }
         }
     }
 
@@ -324,18 +366,7 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
     if (!device_is_sm100()) return set_error(VQB_ENODEVICE, "vqb_conv_gemm: current device is not sm_100");
 
     ConvParams p;  // ~2.5 KB, filled per call, passed by value (__grid_constant__) to the kernel
-    // box of 128 output pixels
-    uint32_t bw = next_pow2(d->W);
-    if (bw > 128) bw = 128;
-    uint32_t bh = next_pow2(d->H);
-    if (bh > 128 / bw) bh = 128 / bw;
-    uint32_t bn = 128 / (bw * bh);
-    p.lbw = ilog2(bw);
-    p.lbh = ilog2(bh);
-    p.lbn = ilog2(bn);
-    p.tiles_w = (d->W + bw - 1) / bw;
-    p.tiles_h = (d->H + bh - 1) / bh;
-    p.tiles_nb = (d->N + bn - 1) / bn;
+    const int p_dbg = debug_mode();
     int block_n;
     if (d->Cout >= 256)
         block_n = 256;
@@ -343,12 +374,50 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
         block_n = ((d->Cout + 15) / 16) * 16;
     p.block_n = block_n;
     p.n_tiles = (d->Cout + block_n - 1) / block_n;
+    // Pixel box per CTA tile: 128*mtiles output pixels. mtiles = 2 shares every weight tile between two 128-row
+    // accumulators (25-33 % less L2->SM traffic per FLOP, the measured limiter); it is used when it does not cost
+    // more in wave quantisation than it gains.
+    auto tiles_for = [&](int mt, uint32_t& bw, uint32_t& bh, uint32_t& bn) {
+        const uint32_t px = 128u * mt;
+        bw = next_pow2(d->W);
+        if (bw > 128) bw = 128;  // <= 256 rows per TMA box dimension; keep W boxes at 128
+        bh = next_pow2(d->H);
+        if (bh > px / bw) bh = px / bw;
+        bn = px / (bw * bh);
+        return static_cast<int64_t>((d->W + bw - 1) / bw) * ((d->H + bh - 1) / bh) * ((d->N + bn - 1) / bn) * p.n_tiles;
+    };
+    uint32_t bw, bh, bn, bw2, bh2, bn2;
+    const int64_t t1 = tiles_for(1, bw, bh, bn);
+    const int64_t t2 = tiles_for(2, bw2, bh2, bn2);
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    // measured gain of the double tile (tools/perf_experiments.py): ~1.15-1.3x when BLOCK_N <= 128 (four TMEM buffers keep
+    // the epilogue fully overlapped), ~1.05x at BLOCK_N = 256, a loss for short K loops (1x1 convs: epilogue bound)
+    const int num_kb_host = d->ntaps * ((d->C + kBlockK - 1) / kBlockK);
+    const double gain = block_n <= 128 ? 1.2 : 1.05;
+    const double cost1 = static_cast<double>((t1 + sms - 1) / sms) * 1.0;
+    const double cost2 = static_cast<double>((t2 + sms - 1) / sms) * 2.0 / gain;
+    int mtiles = (!(p_dbg & 32) && bn2 <= 256 && num_kb_host >= 9 && cost2 < cost1) ? 2 : 1;
+    if (mtiles == 2) {
+        bw = bw2;
+        bh = bh2;
+        bn = bn2;
+    }
+    p.mtiles = mtiles;
+    p.lbw = ilog2(bw);
+    p.lbh = ilog2(bh);
+    p.lbn = ilog2(bn);
+    p.tiles_w = (d->W + bw - 1) / bw;
+    p.tiles_h = (d->H + bh - 1) / bh;
+    p.tiles_nb = (d->N + bn - 1) / bn;
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
-    const int stage_bytes = kABytes + block_n * kBlockK * 2;
+    const int stage_bytes = mtiles * kABytes + block_n * kBlockK * 2;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
-    uint32_t tc = next_pow2(2 * block_n);
+    int nbuf = 512 / block_n;
+    if (nbuf > 4) nbuf = 4;
+    p.nbuf = nbuf;
+    uint32_t tc = next_pow2(nbuf * block_n);
     if (tc < 32) tc = 32;
     p.tmem_cols = tc;
     p.ntaps = d->ntaps;

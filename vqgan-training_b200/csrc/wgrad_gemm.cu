@@ -33,7 +33,7 @@ struct alignas(64) WgradParams {
     int32_t tiles_w, tiles_h, tiles_nb, pixel_boxes;
     int32_t m_tiles, n_tiles, ksplit, total_units;
     int32_t block_n, natoms, stages, tmem_cols;
-    int32_t dbg, kpix, use5d, apl;  // kpix: pixels per K block (64|128); use5d: one TMA per operand; apl: atoms per B load
+    int32_t dbg, kpix, use5d, apl, mtiles;  // mtiles: 128-row Cout sub-tiles per unit (2 = 256x256 tiles, 5-D maps only)  // kpix: pixels per K block (64|128); use5d: one TMA per operand; apl: atoms per B load
     int64_t ld;  // ntaps*C64: row stride of the partial buffer
     float* partial;
 };
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t stages = p.stages;
     const uint32_t atom_bytes = static_cast<uint32_t>(p.kpix) * 128u;  // [kpix px][64 ch] bf16
-    const uint32_t a_bytes = 2 * atom_bytes;
+    const uint32_t a_bytes = 2 * static_cast<uint32_t>(p.mtiles) * atom_bytes;
     const uint32_t b_bytes = static_cast<uint32_t>(p.natoms) * atom_bytes;
     uint8_t* sA = base;
     uint8_t* sB = base + stages * a_bytes;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
         for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
             int m_tile, n_tile, s, kb0, kb1;
             unit_range(unit, m_tile, n_tile, s, kb0, kb1);
-            const int co0 = m_tile * kWM;
+            const int co0 = m_tile * kWM * p.mtiles;
             const int colbase = n_tile * p.block_n;
             const int nkb = kb1 - kb0;
             const int rot = (nkb > 0 && !(p.dbg & 4)) ? static_cast<int>((blockIdx.x * 37u) % static_cast<uint32_t>(nkb)) : 0;
@@ -147,34 +147,59 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
             }
         }
     } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (lean: descriptors are base + increments) =====================
         const uint32_t idesc = make_idesc_bf16(kWM, p.block_n, 1, 1);  // both operands MN-major
-        uint32_t stage = 0, phase = 0, it = 0;
+        // MN-major, 128B swizzle: SBO = 8 K-rows (1024 B), LBO = next 64-wide MN atom (atom_bytes)
+        const uint64_t da_base = make_smem_desc(smem_u32(sA), atom_bytes, 1024, 2);
+        const uint64_t db_base = make_smem_desc(smem_u32(sB), atom_bytes, 1024, 2);
+        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
+        const int ksteps = p.kpix >> 4;
+        const bool do_mma = (p.dbg & 3) != 2;
+        uint32_t stage = 0, phase = 0, it = 0, a_off = 0, b_off = 0;
         for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
             int m_tile, n_tile, s, kb0, kb1;
             unit_range(unit, m_tile, n_tile, s, kb0, kb1);
-            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            // mtiles == 1: double-buffered accumulators (as = it & 1); mtiles == 2: both buffers belong to this unit
+            const bool two = (p.mtiles == 2);
+            const uint32_t as = two ? 0u : (it & 1), aph = two ? (it & 1) : ((it >> 1) & 1);
             mbar_wait(&tempty[as], aph ^ 1);
+            if (two) mbar_wait(&tempty[1], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * p.block_n;
+            const uint32_t d_tmem1 = tmem_base + p.block_n;
+            const uint32_t mt_step = (2 * atom_bytes) >> 4;
+            uint32_t acc = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + stage * a_bytes);
-                const uint32_t b_addr = smem_u32(sB + stage * b_bytes);
-                const int ksteps = p.kpix >> 4;
-                for (int k = 0; k < ksteps; ++k) {
-                    // MN-major, 128B swizzle: SBO = 8 K-rows (1024 B), LBO = next 64-wide MN atom
-                    const uint64_t da = make_smem_desc(a_addr + k * 2048, atom_bytes, 1024, 2);
-                    const uint64_t db = make_smem_desc(b_addr + k * 2048, atom_bytes, 1024, 2);
-                    if ((p.dbg & 3) != 2) umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                const uint64_t da = da_base + a_off, db = db_base + b_off;
+                if (do_mma) {
+                    if (ksteps == 8) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, acc | k);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, acc | k);
+                        if (two) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem1, da + mt_step + 128 * k, db + 128 * k, idesc, acc | k);
+                        }
+                    }
                 }
                 umma_commit(&empty[stage]);
+                acc = 1;
                 if (++stage == stages) {
                     stage = 0;
                     phase ^= 1;
+                    a_off = 0;
+                    b_off = 0;
+                } else {
+                    a_off += a_step;
+                    b_off += b_step;
                 }
             }
+            if (two) umma_commit(&tfull[1]);
             umma_commit(&tfull[as]);
         }
     } else if (warp >= 4) {
@@ -184,8 +209,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
         for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
             int m_tile, n_tile, s, kb0, kb1;
             unit_range(unit, m_tile, n_tile, s, kb0, kb1);
-            const uint32_t as = it & 1, aph = (it >> 1) & 1;
-            const int co = m_tile * kWM + ew * 32 + lane;
+          for (int mt = 0; mt < p.mtiles; ++mt) {
+            const bool two = (p.mtiles == 2);
+            const uint32_t as = two ? static_cast<uint32_t>(mt) : (it & 1), aph = two ? (it & 1) : ((it >> 1) & 1);
+            const int co = (m_tile * p.mtiles + mt) * kWM + ew * 32 + lane;
             const bool valid = co < p.Cout;
             float* orow = p.partial + (static_cast<int64_t>(s) * p.Cout + co) * p.ld + n_tile * p.block_n;
             mbar_wait(&tfull[as], aph);
@@ -211,6 +238,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
             }
             tc_fence_before();
             mbar_arrive(&tempty[as]);
+          }
         }
     }
 
@@ -259,7 +287,11 @@ extern "C" int vqb_wgrad_gemm(const VqbWgradDesc* d, const void* dy, const void*
 
     WgradParams p;
     p.dbg = debug_mode();
-    p.kpix = (p.dbg & 8) ? 64 : 128;  // 128-pixel K blocks: fewer, larger TMA requests (measured 1.75x faster than 64)
+    const bool can5d = (!(p.dbg & 16) && d->C % 64 == 0 && d->Cout % 64 == 0);
+    // 256(Cout) x BLOCK_N tiles with two accumulators when Cout >= 256: each x tile is shared by two dy sub-tiles
+    // (less L2->SM traffic per FLOP); needs the 5-D maps and 64-pixel K blocks to fit three smem stages
+    p.mtiles = (can5d && d->Cout >= 256 && !(p.dbg & 64)) ? 2 : 1;
+    p.kpix = ((p.dbg & 8) || p.mtiles == 2) ? 64 : 128;  // 128-pixel K blocks: fewer, larger TMA requests
     const uint32_t kp = static_cast<uint32_t>(p.kpix);
     uint32_t bw = next_pow2(d->W);
     if (bw > kp) bw = kp;
@@ -287,14 +319,14 @@ extern "C" int vqb_wgrad_gemm(const VqbWgradDesc* d, const void* dy, const void*
         }
     p.block_n = block_n;
     p.natoms = block_n / 64;
-    p.m_tiles = (d->Cout + kWM - 1) / kWM;
+    p.m_tiles = (d->Cout + kWM * p.mtiles - 1) / (kWM * p.mtiles);
     p.n_tiles = cols / block_n;
     p.ksplit = d->ksplit;
     p.total_units = p.m_tiles * p.n_tiles * p.ksplit;
     p.ld = cols;
     p.partial = partial;
     // 5-D (c_lo, w, h, n, c_hi) tensor maps: one TMA request per operand instead of one per 64-channel atom
-    p.use5d = (!(p.dbg & 16) && d->C % 64 == 0 && d->Cout % 64 == 0) ? 1 : 0;
+    p.use5d = can5d ? 1 : 0;
     p.apl = 1;
     if (p.use5d) {
         if (block_n % p.C64 == 0)
@@ -305,7 +337,7 @@ extern "C" int vqb_wgrad_gemm(const VqbWgradDesc* d, const void* dy, const void*
             p.apl = 1;
     }
     const int atom_bytes = p.kpix * 128;
-    const int stage_bytes = 2 * atom_bytes + p.natoms * atom_bytes;
+    const int stage_bytes = 2 * p.mtiles * atom_bytes + p.natoms * atom_bytes;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > kWMaxStages) stages = kWMaxStages;
     p.stages = stages;
@@ -318,7 +350,7 @@ extern "C" int vqb_wgrad_gemm(const VqbWgradDesc* d, const void* dy, const void*
         p.tap_dw[t] = d->taps[t].dw;
         p.tap_dh[t] = d->taps[t].dh;
     }
-    int rc = encode_view(d->dy_view, dy, d->Cout, p.lbw, p.lbh, p.lbn, p.use5d ? 2 : 0, &p.ymap);
+    int rc = encode_view(d->dy_view, dy, d->Cout, p.lbw, p.lbh, p.lbn, p.use5d ? 2 * p.mtiles : 0, &p.ymap);
     if (rc != VQB_OK) return rc;
     for (int v = 0; v < d->nviews; ++v) {
         rc = encode_view(d->views[v], x, d->C, p.lbw, p.lbh, p.lbn, p.use5d ? p.apl : 0, &p.xmap[v]);

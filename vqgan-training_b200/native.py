@@ -80,6 +80,9 @@ def load():
         "vqb_maxpool2_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "vqb_lpips_tail_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
         "vqb_lpips_tail_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "vqb_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+        "vqb_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "vqb_set_debug_mode": (i32, [i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name, None)

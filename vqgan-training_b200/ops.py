@@ -84,8 +84,13 @@ def _wgrad_block_n(cols: int) -> int:
 
 
 def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
+    """Split-K factor of the weight-gradient GEMM: enough (tile, split) units for >= 2 waves of 148 CTAs. Mirrors the
+    tile shape rules of csrc/wgrad_gemm.cu (256-row tiles + 64-pixel K blocks when Cout >= 256, else 128/128)."""
     cols = len(g.taps) * ((g.C + 63) // 64) * 64
-    tiles = ((Cout_pad + 127) // 128) * (cols // _wgrad_block_n(cols))
+    big = Cout_pad >= 256 and g.C % 64 == 0 and Cout_pad % 64 == 0
+    rows = 256 if big else 128
+    kpix = 64 if big else 128
+    tiles = ((Cout_pad + rows - 1) // rows) * (cols // _wgrad_block_n(cols))
 
     def p2(v, cap):
         p = 1
@@ -93,12 +98,12 @@ def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
             p <<= 1
         return min(p, cap)
 
-    bw = p2(g.Wo, 128)  # the kernel walks K in boxes of 128 pixels
-    bh = p2(g.Ho, 128 // bw)
-    bn = 128 // (bw * bh)
+    bw = p2(g.Wo, kpix)
+    bh = p2(g.Ho, kpix // bw)
+    bn = kpix // (bw * bh)
     boxes = -(-g.Wo // bw) * -(-g.Ho // bh) * -(-g.N // bn)
     want = -(-2 * 148 // tiles)
-    return max(1, min(want, max(1, boxes // 2)))
+    return max(1, min(want, max(1, boxes // 4)))
 
 
 def run_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: int, out: torch.Tensor, out_strides,
