@@ -171,6 +171,14 @@ int vqb_attn_fwd(const void* qkv, void* out, float* lse, int N, int T, int C, vo
 int vqb_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* dvec, void* dqkv, int N,
                  int T, int C, void* stream);
 
+/*
+ * VQ codebook nearest neighbour (BASELINE.json config 4; the reference has no VQ — semantics pinned by
+ * oracle/vq_oracle.py): idx[i] = argmin_j sum_c (z[i][c]-e[j][c])^2 in canonical fp32 order (bit-exact vs the oracle,
+ * first index on ties), zq = e[idx], *sqerr += sum (zq - z)^2 when sqerr != NULL.
+ */
+int vqb_vq_argmin(const float* z, const float* e, long long* idx, float* zq, float* sqerr, int M, int K, int D,
+                  void* stream);
+
 /* library / device info */
 const char* vqb_last_error(void);
 int vqb_version(void);

@@ -230,3 +230,45 @@ def test_attention_core_vs_torch_sdpa():
         e_o, e_g = rel_l2(out, ref), rel_l2(qkv.grad, q32.grad)
         print(f"\nattn N={N} T={H * W} C={C}: out rel {e_o:.3e} dqkv rel {e_g:.3e}")
         assert e_o < 1e-2 and e_g < 2e-2
+
+
+def test_vq_argmin_bit_exact_vs_oracle():
+    """Config 4 (parity unpinned by the reference): indices must be BIT-EXACT vs the canonical NumPy oracle, including
+    exact hits, duplicated codes (first index wins) and a ragged row count."""
+    import ops
+    from oracle import vq_oracle as VQ
+
+    rng = np.random.default_rng(1)
+    for (M, K, D) in [(1000, 8192, 16), (33, 100, 4), (4096, 8192, 16), (257, 1024, 64)]:
+        e = rng.uniform(-1.0 / K, 1.0 / K, size=(K, D)).astype(np.float32)
+        z = (rng.standard_normal(size=(M, D)) * (1.0 / K)).astype(np.float32)
+        z[:8] = e[10:18]          # exact hits
+        e[K // 2] = e[3]          # duplicate code: index 3 must win over K//2
+        z[8] = e[3]
+        idx, zq, sq = ops.vq_argmin(torch.from_numpy(z).cuda(), torch.from_numpy(e).cuda())
+        ref_zq, ref_idx, ref_loss, gap = VQ.vq_forward(z, e)
+        got = idx.cpu().numpy()
+        nbad = int((got != ref_idx).sum())
+        print(f"\nvq M={M} K={K} D={D}: mismatches {nbad}, rows with top-2 gap < 1e-6: {(gap < 1e-6).mean():.3f}")
+        assert nbad == 0
+        assert got[8] == 3 and (got[:8] == np.arange(10, 18)).all()
+        assert np.array_equal(zq.cpu().numpy(), ref_zq)
+        ref_sq = float(((ref_zq.astype(np.float64) - z) ** 2).sum())
+        assert abs(sq.item() - ref_sq) <= 1e-4 * max(ref_sq, 1e-12) + 1e-12
+
+
+def test_vector_quantizer_module_straight_through():
+    import ae
+
+    torch.manual_seed(0)
+    vq = ae.VectorQuantizer(n_e=512, e_dim=16, beta=0.25).cuda()
+    z = (torch.randn(2, 16, 8, 8, device="cuda") / 512).requires_grad_(True)
+    zq, loss, idx = vq(z)
+    assert zq.shape == z.shape and idx.shape == (2, 8, 8)
+    (zq.sum() + loss).backward()
+    e = vq.embedding.weight.detach()
+    zq_ref = e[idx.reshape(-1)].view(2, 8, 8, 16).permute(0, 3, 1, 2)
+    assert torch.allclose(zq.detach(), zq_ref, atol=1e-7)
+    g_ref = torch.ones_like(z) + 0.25 * 2 * (z.detach() - zq_ref) / z.numel()  # straight-through + commitment
+    assert torch.allclose(z.grad, g_ref, atol=1e-6)
+    assert vq.embedding.weight.grad is not None and vq.embedding.weight.grad.abs().sum() > 0

@@ -154,7 +154,8 @@ def test_cli_flags_match_reference():
                 "flip_invariance": False, "do_compile": False, "use_wavelet": False,
                 "augment_before_perceptual_loss": False, "downscale_factor": 16, "use_lecam": False,
                 "disc_type": "bce"}
-    assert set(names) == set(expected)
+    extensions = {"use_vq", "vq_codebook_size", "vq_beta"}  # BASELINE config 4; not in the reference
+    assert set(names) - extensions == set(expected) and extensions <= set(names)
     for k, v in expected.items():
         assert names[k].default == v, k
     assert names["do_ganloss"].is_flag and names["do_clamp"].is_flag

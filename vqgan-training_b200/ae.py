@@ -401,3 +401,29 @@ class VAE(nn.Module):
 
 
 AutoEncoder = VAE  # BASELINE.json's name for the same class
+
+
+class VectorQuantizer(nn.Module):
+    """VQ-GAN codebook bottleneck (BASELINE.json config 4). NOT in the reference (it has no codebook anywhere; SURVEY.md
+    fact 1): standard VectorQuantizer semantics pinned by oracle/vq_oracle.py. Drop-in replacement for `VAE.reg`:
+
+        z_q, loss, idx = vq(z)      # z [B, e_dim, h, w] fp32
+        idx  = argmin_j ||z_i - e_j||^2 (canonical fp32 order, first index on ties; csrc/vq.cu)
+        loss = beta * mean((sg[z_q] - z)^2) + mean((z_q - sg[z])^2)
+        z_q  = z + sg[z_q - z]      (straight-through)
+    """
+
+    def __init__(self, n_e: int = 8192, e_dim: int = 16, beta: float = 0.25):
+        super().__init__()
+        self.n_e, self.e_dim, self.beta = n_e, e_dim, beta
+        self.embedding = nn.Embedding(n_e, e_dim)
+        self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)
+
+    def forward(self, z):
+        B, D, H, W = z.shape
+        zf = z.permute(0, 2, 3, 1).reshape(-1, D)
+        idx, _, _ = ops.vq_argmin(zf, self.embedding.weight)
+        zq = self.embedding(idx).view(B, H, W, D).permute(0, 3, 1, 2)
+        loss = self.beta * torch.mean((zq.detach() - z) ** 2) + torch.mean((zq - z.detach()) ** 2)
+        zq = z + (zq - z).detach()
+        return zq, loss, idx.view(B, H, W)

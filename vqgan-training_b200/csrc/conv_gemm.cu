@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const bool has_bias = p.flags & VQB_EPI_BIAS, has_res = p.flags & VQB_EPI_RES;
         const bool do_relu = p.flags & VQB_EPI_RELU, has_mask = p.flags & VQB_EPI_MASK;
         const bool vec_path = (p.oc == 1) && (p.out_f32 == 0);
+        const bool no_store = (p.dbg & 128) != 0;  // experiment: drain TMEM but skip the global stores
         uint32_t ebuf = 0, epar = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.n_tiles;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
             const int ni = row >> (p.lbw + p.lbh);
             const int w = (tw << p.lbw) + wi, h = (th << p.lbh) + hi, n = (tn << p.lbn) + ni;
-            const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+            const bool valid = (w < p.W) && (h < p.H) && (n < p.N) && !no_store;
             const int64_t pix = static_cast<int64_t>(n) * p.on + static_cast<int64_t>(h) * p.oh +
                                 static_cast<int64_t>(w) * p.ow;
 

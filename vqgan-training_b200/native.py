@@ -83,6 +83,7 @@ def load():
         "vqb_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp]),
         "vqb_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "vqb_set_debug_mode": (i32, [i32]),
+        "vqb_vq_argmin": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name, None)

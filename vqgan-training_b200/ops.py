@@ -421,3 +421,17 @@ class LpipsTailFn(torch.autograd.Function):
 
 def lpips_tail(f0, f1, w):
     return LpipsTailFn.apply(f0, f1, w)
+
+
+def vq_argmin(z_flat: torch.Tensor, codebook: torch.Tensor):
+    """z_flat [M, D] fp32, codebook [K, D] fp32 -> (idx int64 [M], zq fp32 [M, D], sum of squared errors (0-dim))."""
+    require_cuda(z_flat)
+    z_flat = z_flat.detach().float().contiguous()
+    cb = codebook.detach().float().contiguous()
+    M, D = z_flat.shape
+    idx = torch.empty(M, device=z_flat.device, dtype=torch.int64)
+    zq = torch.empty_like(z_flat)
+    sq = torch.zeros((), device=z_flat.device, dtype=torch.float32)
+    check(_L().vqb_vq_argmin(ptr(z_flat), ptr(cb), ptr(idx), ptr(zq), ptr(sq), M, cb.shape[0], D, stream_ptr()),
+          "vq_argmin")
+    return idx, zq, sq

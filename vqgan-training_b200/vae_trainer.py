@@ -254,7 +254,7 @@ class Trainer:
                  use_wavelet=False, do_ganloss=False, learning_rate_vae=1e-5, learning_rate_disc=2e-4, max_steps=1000,
                  do_clamp=False, clamp_th=8.0, crop_invariance=False, flip_invariance=False,
                  augment_before_perceptual_loss=False, downscale_factor=16, use_lecam=False, disc_type="bce",
-                 lpips_eval=True, seed=42):
+                 lpips_eval=True, seed=42, use_vq=False, vq_codebook_size=8192, vq_beta=0.25):
         self.device = device
         self.do_ganloss, self.do_clamp, self.clamp_th = do_ganloss, do_clamp, clamp_th
         self.crop_invariance, self.flip_invariance = crop_invariance, flip_invariance
@@ -271,6 +271,11 @@ class Trainer:
                   ch_mult=[int(x) for x in str(vae_ch_mult).split(",")], num_res_blocks=vae_num_res_blocks,
                   z_channels=vae_z_channels, use_attn=do_attn, decoder_also_perform_hr=decoder_also_perform_hr,
                   use_wavelet=use_wavelet).to(device)
+        self.use_vq = use_vq
+        if use_vq:  # BASELINE.json config 4: the codebook replaces vae.module.reg (vae_trainer.py:563)
+            from ae import VectorQuantizer
+
+            vae.reg = VectorQuantizer(vq_codebook_size, vae_z_channels, vq_beta).to(device)
         discriminator = PatchDiscriminator().to(device)
         discriminator.requires_grad_(True)
         self.vae = FlatAllReduceDDP(vae)
@@ -310,7 +315,11 @@ class Trainer:
         z_for_stats = z.detach()
         if self.do_clamp:
             z = z.clamp(-self.clamp_th, self.clamp_th)
-        z_s = vae.module.reg(z)
+        vq_loss = None
+        if self.use_vq:
+            z_s, vq_loss, _ = vae.module.reg(z)
+        else:
+            z_s = vae.module.reg(z)
 
         if random.random() < 0.5 and self.flip_invariance:  # :567-570
             z_s = torch.flip(z_s, [-1]).clone()
@@ -386,6 +395,9 @@ class Trainer:
             out["g_gan_loss"] = g_gan_loss.detach()
         else:
             overall_vae_loss = percep_rec_loss + vae_loss
+        if vq_loss is not None:
+            overall_vae_loss = overall_vae_loss + vq_loss
+            out["vq_loss"] = vq_loss.detach()
 
         overall_vae_loss.backward()  # :701
         vae.allreduce_grads()        # the all-reduce the reference intends
@@ -442,11 +454,14 @@ class Trainer:
 @click.option("--downscale_factor", type=int, default=16, help="Downscale factor for the latent space")
 @click.option("--use_lecam", type=bool, default=False, help="Whether to use Lecam")
 @click.option("--disc_type", type=str, default="bce", help="Discriminator type")
+@click.option("--use_vq", type=bool, default=False, help="[extension] VQ codebook bottleneck instead of reg (BASELINE config 4)")
+@click.option("--vq_codebook_size", type=int, default=8192, help="[extension] number of codebook entries")
+@click.option("--vq_beta", type=float, default=0.25, help="[extension] commitment loss weight")
 def train_ddp(dataset_url, test_dataset_url, num_epochs, batch_size, do_ganloss, learning_rate_vae, learning_rate_disc,
               vae_resolution, vae_in_channels, vae_ch, vae_ch_mult, vae_num_res_blocks, vae_z_channels, run_name,
               max_steps, evaluate_every_n_steps, load_path, do_clamp, clamp_th, max_spatial_dim, do_attn,
               decoder_also_perform_hr, project_name, crop_invariance, flip_invariance, do_compile, use_wavelet,
-              augment_before_perceptual_loss, downscale_factor, use_lecam, disc_type):
+              augment_before_perceptual_loss, downscale_factor, use_lecam, disc_type, use_vq, vq_codebook_size, vq_beta):
     assert torch.cuda.is_available(), "CUDA is required for DDP"
     ddp_rank = int(os.environ.get("RANK", "0"))
     ddp_local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -470,7 +485,8 @@ def train_ddp(dataset_url, test_dataset_url, num_epochs, batch_size, do_ganloss,
     tr = Trainer(device, vae_resolution, vae_in_channels, vae_ch, vae_ch_mult, vae_num_res_blocks, vae_z_channels,
                  do_attn, decoder_also_perform_hr, use_wavelet, do_ganloss, learning_rate_vae, learning_rate_disc,
                  max_steps, do_clamp, clamp_th, crop_invariance, flip_invariance, augment_before_perceptual_loss,
-                 downscale_factor, use_lecam, disc_type, lpips_eval=False)
+                 downscale_factor, use_lecam, disc_type, lpips_eval=False, use_vq=use_vq,
+                 vq_codebook_size=vq_codebook_size, vq_beta=vq_beta)
 
     logger = logging.getLogger(__name__)
     logger.setLevel(logging.INFO)
