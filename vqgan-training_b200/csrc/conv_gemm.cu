@@ -27,6 +27,7 @@ constexpr int kMaxStages = 8;
 struct alignas(64) ConvParams {
     CUtensorMap amap[VQB_MAX_VIEWS];
     CUtensorMap bmap;
+    CUtensorMap omap;  // output tensor (TMA-store epilogue)
     int32_t tap_view[VQB_MAX_TAPS];
     int32_t tap_dw[VQB_MAX_TAPS];
     int32_t tap_dh[VQB_MAX_TAPS];
@@ -36,7 +37,8 @@ struct alignas(64) ConvParams {
     int32_t tiles_w, tiles_h, tiles_nb;
     int32_t n_tiles, total_tiles;
     int32_t block_n, stages, tmem_cols;
-    int32_t mtiles, nbuf;  // 128-row accumulator sub-tiles per CTA tile (1|2); TMEM accumulator buffers (2..4)
+    int32_t mtiles, nbuf;
+    int32_t tma_store, mt_dh, mt_dn, _pad1;  // TMA-store epilogue enabled; box offset of the second sub-tile  // 128-row accumulator sub-tiles per CTA tile (1|2); TMEM accumulator buffers (2..4)
     int32_t flags, out_f32;
     int32_t dbg, _pad0;
     int64_t on, oh, ow, oc;
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t mtiles = p.mtiles, nbuf = p.nbuf;
     uint8_t* sA = base;
     uint8_t* sB = base + stages * a_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_bytes);
+    uint8_t* sOut = sB + stages * b_bytes;  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (p.tma_store ? 2 * 16384 : 0));
     uint64_t* empty = full + stages;
     uint64_t* tfull = empty + stages;
     uint64_t* tempty = tfull + 4;
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (used) tma_prefetch_desc(&p.amap[v]);
         }
         tma_prefetch_desc(&p.bmap);
+        if (p.tma_store) tma_prefetch_desc(&p.omap);
     }
     if (warp == 1 && lane == 0) {
         for (uint32_t i = 0; i < stages; ++i) {
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const bool do_relu = p.flags & VQB_EPI_RELU, has_mask = p.flags & VQB_EPI_MASK;
         const bool vec_path = (p.oc == 1) && (p.out_f32 == 0);
         const bool no_store = (p.dbg & 128) != 0;  // experiment: drain TMEM but skip the global stores
-        uint32_t ebuf = 0, epar = 0;
+        uint32_t ebuf = 0, epar = 0, obuf = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.n_tiles;
           const int m_tile = tile / p.n_tiles;
@@ -232,6 +236,95 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + as * p.block_n;
+            if (p.tma_store) {
+                // -------- staged epilogue: registers -> 128B-swizzled smem tile -> one TMA store per 64 channels.
+                // (direct per-thread stores write 32 B per lane at a 2*Cout-byte pitch: measured to cost up to half of the
+                // kernel time on short-K layers)
+                const int ow0 = tw << p.lbw;
+                const int oh0 = (th << p.lbh) + (mt ? p.mt_dh : 0);
+                const int on0 = (tn << p.lbn) + (mt ? p.mt_dn : 0);
+                const uint32_t r = ew * 32 + lane;
+                const int ngroups = (p.block_n + 63) >> 6;
+                for (int cg = 0; cg < ngroups; ++cg) {
+                    if (col0 + cg * 64 >= p.Cout) break;  // uniform
+                    uint8_t* sbuf = sOut + (obuf & 1u) * 16384u;
+                    if (ew == 0 && lane == 0) bulk_wait_read<1>();  // the store issued from this buffer has drained it
+                    named_bar_sync(1, 128);
+                    // both 32-column TMEM loads of this group are issued before the single wait (latency overlap)
+                    uint32_t v0[32], v1[32];
+                    const int cbase = cg * 64;
+                    const bool h0 = cbase < p.block_n, h1 = cbase + 32 < p.block_n;  // uniform
+                    if (h0) tmem_ld32(taddr + cbase, v0);
+                    if (h1) tmem_ld32(taddr + cbase + 32, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int c0 = cbase + c4 * 16;
+                        const int col = col0 + c0;
+                        float f[16];
+                        const bool have = (c4 < 2) ? h0 : h1;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t raw = (c4 < 2) ? v0[(c4 & 1) * 16 + j] : v1[(c4 & 1) * 16 + j];
+                            f[j] = have ? __uint_as_float(raw) : 0.f;
+                        }
+                        const bool live = (col + 16 <= p.Cout);  // uniform (Cout % 16 == 0 on this path)
+                        if (live) {
+                            if (has_bias) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+                            }
+                            if (has_res && valid) {
+                                const uint4* rp = reinterpret_cast<const uint4*>(
+                                    reinterpret_cast<const __nv_bfloat16*>(p.res) + pix + col);
+                                uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float2 t = unpack_bf16x2(rr[j]);
+                                    f[2 * j] += t.x;
+                                    f[2 * j + 1] += t.y;
+                                }
+                            }
+                            if (do_relu) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                            }
+                            if (has_mask && valid) {
+                                const uint4* mp = reinterpret_cast<const uint4*>(
+                                    reinterpret_cast<const __nv_bfloat16*>(p.mask) + pix + col);
+                                uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                                const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float2 t = unpack_bf16x2(mm[j]);
+                                    if (!(t.x > 0.f)) f[2 * j] = 0.f;
+                                    if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
+                                }
+                            }
+                        }
+                        uint4 o0, o1;
+                        o0.x = pack_bf16x2(f[0], f[1]);
+                        o0.y = pack_bf16x2(f[2], f[3]);
+                        o0.z = pack_bf16x2(f[4], f[5]);
+                        o0.w = pack_bf16x2(f[6], f[7]);
+                        o1.x = pack_bf16x2(f[8], f[9]);
+                        o1.y = pack_bf16x2(f[10], f[11]);
+                        o1.z = pack_bf16x2(f[12], f[13]);
+                        o1.w = pack_bf16x2(f[14], f[15]);
+                        uint8_t* rowp = sbuf + r * 128u;
+                        *reinterpret_cast<uint4*>(rowp + (((2 * c4) ^ (r & 7u)) << 4)) = o0;
+                        *reinterpret_cast<uint4*>(rowp + (((2 * c4 + 1) ^ (r & 7u)) << 4)) = o1;
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (ew == 0 && lane == 0 && !no_store) {
+                        tma_store_4d(&p.omap, sbuf, col0 + cg * 64, ow0, oh0, on0);
+                        bulk_commit();
+                    }
+                    ++obuf;
+                }
+            } else
             for (int c0 = 0; c0 < p.block_n; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
@@ -315,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_arrive(&tempty[as]);
           }
         }
+        if (p.tma_store && ew == 0 && lane == 0) bulk_wait_all();  // smem must outlive the last bulk stores
     }
 
     tc_fence_before();
@@ -411,8 +505,23 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
     p.tiles_h = (d->H + bh - 1) / bh;
     p.tiles_nb = (d->N + bn - 1) / bn;
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
+    // TMA-store epilogue: NHWC bf16 outputs (any pixel strides) with Cout % 16 == 0
+    const bool tma_store = (d->oc == 1) && !d->out_f32 && (d->Cout % 16 == 0) && (block_n % 32 == 0) && !(p_dbg & 256);
+    p.tma_store = tma_store ? 1 : 0;
+    p.mt_dh = 0;
+    p.mt_dn = 0;
+    uint32_t obw = bw, obh = bh, obn = bn;  // 128-pixel store box = one accumulator sub-tile
+    if (mtiles == 2) {
+        if (bn >= 2) {
+            obn = bn / 2;
+            p.mt_dn = static_cast<int32_t>(obn);
+        } else {
+            obh = bh / 2;
+            p.mt_dh = static_cast<int32_t>(obh);
+        }
+    }
     const int stage_bytes = mtiles * kABytes + block_n * kBlockK * 2;
-    int stages = (200 * 1024) / stage_bytes;
+    int stages = (227 * 1024 - 1280 - (tma_store ? 2 * 16384 : 0)) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
     int nbuf = 512 / block_n;
@@ -455,7 +564,16 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
         rc = encode_tmap_bf16(&p.bmap, w_packed, 2, dims, str, box, 128);
         if (rc != VQB_OK) return rc;
     }
-    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256;
+    if (tma_store) {
+        uint64_t dims[4] = {static_cast<uint64_t>(d->Cout), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                            static_cast<uint64_t>(d->N)};
+        uint64_t str[3] = {static_cast<uint64_t>(d->ow) * 2, static_cast<uint64_t>(d->oh) * 2,
+                           static_cast<uint64_t>(d->on) * 2};
+        uint32_t box[4] = {64, obw, obh, obn};
+        rc = encode_tmap_bf16(&p.omap, out, 4, dims, str, box, 128);
+        if (rc != VQB_OK) return rc;
+    }
+    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (tma_store ? 2 * 16384 : 0) + 256;
     static bool attr_set = false;
     if (!attr_set) {
         VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

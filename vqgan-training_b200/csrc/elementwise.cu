@@ -493,14 +493,27 @@ static inline int cv_threads(int C) {
     if (t < V) t = V;
     return t;
 }
-static inline void cv_grid(int HW, int C, int N, int& chunks, int& pix_per_chunk) {
+// Grid for the fixed-channel-vector kernels: (chunks, N) blocks of cv_threads(C) threads. The block count is made a
+// whole number of waves for the kernel's actual occupancy (these kernels are HBM bound; a 60 %-full second wave was
+// costing ~20 %), with at least 4 row-iterations of work per thread.
+template <typename Kernel>
+static inline void cv_grid(int HW, int C, int N, Kernel kernel, size_t smem, int& chunks, int& pix_per_chunk) {
     const int V = C / 8;
     const int T = cv_threads(C);
     const int R = T / V > 0 ? T / V : 1;
-    // aim for >= 4 waves of 148 SMs overall, but at least 4 row-iterations per thread
-    int want = (148 * 8 + N - 1) / N;
-    int ppc = (HW + want - 1) / want;
+    int bpsm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kernel, T, smem) != cudaSuccess || bpsm < 1) bpsm = 4;
+    const int concurrent = (num_sms() > 0 ? num_sms() : 148) * bpsm;
     const int min_ppc = R * 4;
+    int best_chunks = 1;
+    for (int waves = 1; waves <= 8; ++waves) {
+        int c = (concurrent * waves) / N;  // chunks per image so that N*c <= waves*concurrent
+        if (c < 1) c = 1;
+        const int ppc = (HW + c - 1) / c;
+        best_chunks = c;
+        if (ppc <= 2048 || ppc <= min_ppc) break;  // small enough pieces: stop adding waves
+    }
+    int ppc = (HW + best_chunks - 1) / best_chunks;
     if (ppc < min_ppc) ppc = min_ppc;
     ppc = ((ppc + R - 1) / R) * R;
     pix_per_chunk = ppc;
@@ -556,11 +569,12 @@ int vqb_gn_silu_fwd(const void* x, void* y, const float* gamma, const float* bet
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VQB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * C, st));
     int chunks, ppc;
-    cv_grid(HW, C, N, chunks, ppc);
     const int T = cv_threads(C);
+    cv_grid(HW, C, N, gn_stats_kernel, 2 * C * sizeof(float), chunks, ppc);
     gn_stats_kernel<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x), ws, HW, C,
                                                                         ppc);
     gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(ws, mr, N, C, G, HW, eps);
+    cv_grid(HW, C, N, gn_apply_kernel, 0, chunks, ppc);
     gn_apply_kernel<<<dim3(chunks, N), T, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
                                                    static_cast<__nv_bfloat16*>(y), mr, gamma, beta, HW, C, G, ppc,
                                                    silu);
@@ -580,13 +594,14 @@ int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, co
     float* gsum = ws + static_cast<int64_t>(N) * C * 2;
     VQB_CUDA(cudaMemsetAsync(cs, 0, sizeof(float) * 2 * N * C, st));
     int chunks, ppc;
-    cv_grid(HW, C, N, chunks, ppc);
     const int T = cv_threads(C);
+    cv_grid(HW, C, N, gn_bwd_reduce_kernel, 2 * C * sizeof(float), chunks, ppc);
     gn_bwd_reduce_kernel<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mr, gamma, beta, cs, HW, C, G,
         ppc, silu);
     const int fin = (N * G > C ? N * G : C);
     gn_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(cs, gamma, gsum, dgamma, dbeta, N, C, G, HW);
+    cv_grid(HW, C, N, gn_bwd_apply_kernel, 0, chunks, ppc);
     gn_bwd_apply_kernel<<<dim3(chunks, N), T, 0, st>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
         static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), mr, gsum, gamma, beta, HW, C, G, ppc,
@@ -622,7 +637,13 @@ int vqb_colsum(const void* x, float* out, int64_t P, int C, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VQB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
     const int V = C / 8, T = cv_threads(C), R = T / V;
-    int64_t ppc = (P + 148 * 8 - 1) / (148 * 8);
+    int bpsm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, colsum_kernel, T, C * sizeof(float)) != cudaSuccess || bpsm < 1)
+        bpsm = 4;
+    const int64_t concurrent = static_cast<int64_t>(num_sms() > 0 ? num_sms() : 148) * bpsm;
+    int64_t nblk = concurrent;
+    while (nblk < concurrent * 8 && (P + nblk - 1) / nblk > 2048) nblk += concurrent;
+    int64_t ppc = (P + nblk - 1) / nblk;
     if (ppc < R * 4) ppc = R * 4;
     ppc = ((ppc + R - 1) / R) * R;
     const int chunks = static_cast<int>((P + ppc - 1) / ppc);

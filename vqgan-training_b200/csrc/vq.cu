@@ -12,11 +12,10 @@
 namespace vqb {
 
 constexpr int kVqRowsPerBlock = 32;  // 8 warps x 4 rows
-constexpr int kVqChunk = 1024;       // codes per smem chunk
 
 __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ e,
                                                         long long* __restrict__ idx, float* __restrict__ zq,
-                                                        float* __restrict__ sqerr, int M, int K, int D) {
+                                                        float* __restrict__ sqerr, int M, int K, int D, int kVqChunk) {
     extern __shared__ float sm[];
     float* zs = sm;                             // [32][D]
     float* cs = sm + kVqRowsPerBlock * D;       // [chunk][D+1]
@@ -102,6 +101,9 @@ int vqb_vq_argmin(const float* z, const float* e, long long* idx, float* zq, flo
                   void* stream) {
     VQB_CHECK(z && e && idx && zq, "vqb_vq_argmin: null pointer");
     VQB_CHECK(M > 0 && K > 0 && D > 0 && D <= 256, "vqb_vq_argmin: bad sizes M=%d K=%d D=%d", M, K, D);
+    int kVqChunk = 1024;  // codes per shared-memory chunk (smaller for wide codes)
+    while (kVqChunk > 32 && (static_cast<size_t>(kVqRowsPerBlock) * D + static_cast<size_t>(kVqChunk) * (D + 1)) * sizeof(float) > 160 * 1024)
+        kVqChunk >>= 1;
     const size_t smem = (static_cast<size_t>(kVqRowsPerBlock) * D + static_cast<size_t>(kVqChunk) * (D + 1)) * sizeof(float);
     VQB_CHECK(smem <= 200 * 1024, "vqb_vq_argmin: D=%d too large for the shared-memory chunk", D);
     static size_t attr_set = 0;
@@ -112,7 +114,7 @@ int vqb_vq_argmin(const float* z, const float* e, long long* idx, float* zq, flo
     int blocks = (M + kVqRowsPerBlock - 1) / kVqRowsPerBlock;
     const int cap = (num_sms() > 0 ? num_sms() : 148) * 2;
     if (blocks > cap) blocks = cap;
-    vq_argmin_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(z, e, idx, zq, sqerr, M, K, D);
+    vq_argmin_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(z, e, idx, zq, sqerr, M, K, D, kVqChunk);
     VQB_CUDA(cudaGetLastError());
     count_launch();
     return VQB_OK;

@@ -102,8 +102,20 @@ def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
     bh = p2(g.Ho, kpix // bw)
     bn = kpix // (bw * bh)
     boxes = -(-g.Wo // bw) * -(-g.Ho // bh) * -(-g.N // bn)
-    want = -(-2 * 148 // tiles)
-    return max(1, min(want, max(1, boxes // 4)))
+    # pick the split count whose (tile, split) unit count fills whole waves of 148 persistent CTAs best (a 2.2-wave
+    # launch runs as long as a 3-wave one), with >= 4 K-blocks per unit and a bounded fp32 partial buffer
+    sms = 148
+    max_ks = max(1, min(boxes // 4, 128, (256 << 20) // max(1, Cout_pad * cols * 4)))
+    best, best_score = 1, -1.0
+    for ks in range(1, max_ks + 1):
+        units = tiles * ks
+        waves = -(-units // sms)
+        eff = units / (waves * sms)
+        # mild preference for >= 2 waves (hides the per-unit prologue/epilogue) and against needless splitting
+        score = eff - (0.08 if waves < 2 else 0.0) - 0.002 * ks
+        if score > best_score:
+            best, best_score = ks, score
+    return best
 
 
 def run_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: int, out: torch.Tensor, out_strides,
