@@ -306,7 +306,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    prof = profile_conv_kernels(tr, dev_batches[0]) if rank == 0 else None
+    # every rank runs the profiled extra step (it contains the NCCL collectives of a normal step); rank 0 reports it
+    prof = profile_conv_kernels(tr, dev_batches[0])
 
     if rank == 0:
         peak, peak_src = load_peaks()

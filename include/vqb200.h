@@ -92,7 +92,9 @@ typedef struct VqbWgradDesc {
     int32_t N, H, W; /* dy pixel grid                       */
     int32_t nviews, ntaps;
     int32_t ksplit;
-    VqbView dy_view; /* normally the dense view of dy       */
+    int64_t ld_override; /* row pitch (floats) of partial; 0 = ntaps*roundup(C,64)                     */
+    int64_t col_offset;  /* first column of partial this launch writes (several launches, one buffer) */
+    VqbView dy_view;     /* normally the dense view of dy                                              */
     VqbView views[VQB_MAX_VIEWS];
     VqbTap taps[VQB_MAX_TAPS];
 } VqbWgradDesc;
@@ -123,6 +125,12 @@ int vqb_pack_weights(const float* w_oihw, void* out, int Cout, int Cin, int T, i
  * channels (pad = 0); shift/inv_scale may be NULL. The scaled form is LPIPS/PatchD ScalingLayer (utils.py:70-71).
  * vqb_nhwc_to_nchw is the inverse / the backward of it (gx = g * inv_scale).
  */
+/* folded variants (slot -> SET of taps as a bit mask): nearest-2x upsample fused into 4 phase convs with 2x2 taps */
+int vqb_pack_weights_fold(const float* w_oihw, void* out, int Cout, int Cin, int T, int nslots, const int* tapmask_dev,
+                          int transpose, int Kpad, void* stream);
+int vqb_wgrad_reduce_fold(const float* partial, float* grad, int ksplit, int Cout, int CoutPad, int Cin, int T,
+                          int nslots, int C64, const int* tapmask_dev, void* stream);
+
 int vqb_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cpad, const float* shift,
                      const float* inv_scale, void* stream);
 int vqb_nhwc_to_nchw(const void* g, float* gx, int N, int C, int H, int W, int Cpad, const float* inv_scale,

@@ -69,4 +69,4 @@ def test_struct_layout_matches_header(lib):
     assert ctypes.sizeof(native.VqbView) == 48
     assert ctypes.sizeof(native.VqbTap) == 16
     assert ctypes.sizeof(native.VqbConvDesc) == 40 + 32 + 16 * 48 + 16 * 16
-    assert ctypes.sizeof(native.VqbWgradDesc) == 32 + 48 + 16 * 48 + 16 * 16
+    assert ctypes.sizeof(native.VqbWgradDesc) == 32 + 16 + 48 + 16 * 48 + 16 * 16

@@ -193,3 +193,29 @@ torch.save(m.state_dict(), sys.argv[1])
     assert set(mine) == set(ref_sd)
     for k in ref_sd:
         assert torch.equal(mine[k], ref_sd[k]), k
+
+
+def test_geom_upsample_fold_matches_nearest_upsample_conv():
+    """Folded 2x2 phase convs == conv3x3(nearest_x2(x)) incl. the dgrad geometry."""
+    torch.manual_seed(5)
+    N, h, w, C, Co = 1, 4, 5, 8, 8
+    x, wt = torch.randn(N, h, w, C), torch.randn(Co, C, 3, 3)
+    ref = F.conv2d(F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"), wt, padding=1)
+    out = torch.zeros(N, 2 * h, 2 * w, Co)
+
+    def fold(mask_list, transpose):
+        wf = torch.stack([sum(wt.reshape(Co, C, 9)[:, :, t] for t in range(9) if (m >> t) & 1) for m in mask_list], 2)
+        return wf.permute(1, 2, 0).contiguous() if transpose else wf.permute(0, 2, 1).contiguous()  # [R][slot][K]
+
+    for ph in range(2):
+        for pw in range(2):
+            g = plans.geom_up_fwd(N, h, w, C, ph, pw)
+            out[:, ph::2, pw::2, :] = emulate_conv_gemm(g, x, fold(g.tapmask, False), Co)
+    assert torch.allclose(out, ref.permute(0, 2, 3, 1), atol=1e-4)
+    dy = torch.randn(N, 2 * h, 2 * w, Co)
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    y = F.conv2d(F.interpolate(xr, scale_factor=2.0, mode="nearest"), wt, padding=1)
+    (gref,) = torch.autograd.grad(y, xr, dy.permute(0, 3, 1, 2))
+    gd = plans.geom_up_dgrad(N, h, w, Co)
+    gx = emulate_conv_gemm(gd, dy, fold(gd.tapmask, True), C)
+    assert torch.allclose(gx, gref.permute(0, 2, 3, 1), atol=1e-4)

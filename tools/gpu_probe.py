@@ -406,6 +406,32 @@ def group_lpips():
     return ok
 
 
+def group_up():
+    """nearest-2x upsample + conv3x3 folded into 4 phase convs (ops.UpConvFn) vs F.interpolate + F.conv2d autograd."""
+    import ops
+    ok = True
+    torch.manual_seed(0)
+    for (N, h, w, Ci, Co) in [(2, 16, 16, 128, 128), (1, 32, 32, 256, 256), (2, 8, 8, 64, 64), (1, 12, 20, 64, 128)]:
+        x = rnd(N, h, w, Ci).to(torch.bfloat16).requires_grad_(True)
+        wt = (rnd(Co, Ci, 3, 3) * (Ci * 9) ** -0.5).requires_grad_(True)
+        b = rnd(Co).requires_grad_(True)
+        cache = ops.PackedCache()
+        y = ops.upsample_conv(x, wt, b, cache)
+        gy = rnd(N, 2 * h, 2 * w, Co).to(torch.bfloat16)
+        y.backward(gy)
+        xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        wr = wt.detach().clone().requires_grad_(True)
+        br = b.detach().clone().requires_grad_(True)
+        yr = F.conv2d(F.interpolate(xr, scale_factor=2.0, mode="nearest"), wr, br, padding=1)
+        yr.backward(gy.float().permute(0, 3, 1, 2))
+        tag = f"upconv N={N} {h}x{w} {Ci}->{Co}"
+        ok &= report(tag + " fwd", y, yr.permute(0, 2, 3, 1), tol=1e-2)  # folded weights are rounded after the fp32 sum
+        ok &= report("   dx", x.grad, xr.grad.permute(0, 2, 3, 1), tol=1e-2)
+        ok &= report("   dW", wt.grad.reshape(Co, -1), wr.grad.reshape(Co, -1), tol=1e-2)
+        ok &= report("   db", b.grad[None], br.grad[None], tol=1e-2)
+    return ok
+
+
 def group_gemm():
     ok = True
     ok &= case_gemm(128, 64, 16)

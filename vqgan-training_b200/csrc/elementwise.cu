@@ -55,6 +55,31 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     }
 }
 
+// Folded packing: out[r][slot][k] = sum over the taps in tapmask[slot] (bit t = tap t) of w[..][tap]; the fp32 sum is
+// rounded to bf16 once. Used by the nearest-2x-upsample + conv3x3 fusion (4 phase convs with 2x2 folded taps).
+__global__ void pack_weights_fold_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
+                                         int Cin, int T, int nslots, const int* __restrict__ tapmask, int transpose,
+                                         int Kpad) {
+    const int R = transpose ? Cin : Cout;
+    const int K = transpose ? Cout : Cin;
+    const int64_t total = static_cast<int64_t>(R) * nslots * Kpad;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % Kpad);
+        const int slot = static_cast<int>((i / Kpad) % nslots);
+        const int r = static_cast<int>(i / (static_cast<int64_t>(Kpad) * nslots));
+        float v = 0.f;
+        if (k < K) {
+            const int mask = tapmask[slot];
+            const int co = transpose ? k : r, ci = transpose ? r : k;
+            const float* wp = w + (static_cast<int64_t>(co) * Cin + ci) * T;
+            for (int t = 0; t < T; ++t)
+                if ((mask >> t) & 1) v += wp[t];
+        }
+        out[i] = __float2bfloat16(v);
+    }
+}
+
 // ------------------------------------------------------------------ layout conversion
 // y[n,h,w,c] = (x[n,c,h,w] - shift[c]) * inv_scale[c]   (bf16 NHWC, channels >= C zero)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int HW,
@@ -478,6 +503,27 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
 }
 
+// Folded variant: slot s contributes to every tap in tapmask[s] (transpose of pack_weights_fold).
+__global__ void wgrad_reduce_fold_kernel(const float* __restrict__ partial, float* __restrict__ grad, int ksplit,
+                                         int Cout, int CoutPad, int Cin, int T, int nslots, int C64,
+                                         const int* __restrict__ tapmask) {
+    const int64_t total = static_cast<int64_t>(Cout) * Cin * T;
+    const int64_t ld = static_cast<int64_t>(nslots) * C64;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % Cin);
+        const int tap = static_cast<int>((i / Cin) % T);
+        const int co = static_cast<int>(i / (static_cast<int64_t>(T) * Cin));
+        float acc = 0.f;
+        for (int slot = 0; slot < nslots; ++slot) {
+            if (!((tapmask[slot] >> tap) & 1)) continue;
+            for (int s = 0; s < ksplit; ++s)
+                acc += partial[(static_cast<int64_t>(s) * CoutPad + co) * ld + static_cast<int64_t>(slot) * C64 + ci];
+        }
+        grad[(static_cast<int64_t>(co) * Cin + ci) * T + tap] = acc;
+    }
+}
+
 static inline int gs_blocks(int64_t total, int threads) {
     int64_t b = (total + threads - 1) / threads;
     const int64_t cap = static_cast<int64_t>(num_sms() > 0 ? num_sms() : 148) * 16;
@@ -534,6 +580,30 @@ int vqb_pack_weights(const float* w, void* out, int Cout, int Cin, int T, int ns
     const int64_t total = static_cast<int64_t>(R) * nslots * Kpad;
     pack_weights_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w, static_cast<__nv_bfloat16*>(out), Cout, Cin, T, nslots, tapmap_dev, transpose, Kpad, 0);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+int vqb_pack_weights_fold(const float* w, void* out, int Cout, int Cin, int T, int nslots, const int* tapmask_dev,
+                          int transpose, int Kpad, void* stream) {
+    VQB_CHECK(w && out && tapmask_dev, "vqb_pack_weights_fold: null pointer");
+    VQB_CHECK(Kpad % 8 == 0 && Kpad >= (transpose ? Cout : Cin) && T <= 31, "vqb_pack_weights_fold: bad Kpad/T");
+    const int R = transpose ? Cin : Cout;
+    const int64_t total = static_cast<int64_t>(R) * nslots * Kpad;
+    pack_weights_fold_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(out), Cout, Cin, T, nslots, tapmask_dev, transpose, Kpad);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+int vqb_wgrad_reduce_fold(const float* partial, float* grad, int ksplit, int Cout, int CoutPad, int Cin, int T,
+                          int nslots, int C64, const int* tapmask_dev, void* stream) {
+    VQB_CHECK(partial && grad && tapmask_dev && T <= 31, "vqb_wgrad_reduce_fold: bad arguments");
+    const int64_t total = static_cast<int64_t>(Cout) * Cin * T;
+    wgrad_reduce_fold_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        partial, grad, ksplit, Cout, CoutPad, Cin, T, nslots, C64, tapmask_dev);
     VQB_CUDA(cudaGetLastError());
     count_launch();
     return VQB_OK;

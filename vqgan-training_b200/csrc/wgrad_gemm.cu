@@ -323,8 +323,9 @@ extern "C" int vqb_wgrad_gemm(const VqbWgradDesc* d, const void* dy, const void*
     p.n_tiles = cols / block_n;
     p.ksplit = d->ksplit;
     p.total_units = p.m_tiles * p.n_tiles * p.ksplit;
-    p.ld = cols;
-    p.partial = partial;
+    // ld_override / col_offset: several launches may fill column ranges of one partial buffer (folded upsample conv)
+    p.ld = d->ld_override > 0 ? d->ld_override : cols;
+    p.partial = partial + d->col_offset;
     // 5-D (c_lo, w, h, n, c_hi) tensor maps: one TMA request per operand instead of one per 64-channel atom
     p.use5d = can5d ? 1 : 0;
     p.apl = 1;

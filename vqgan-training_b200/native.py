@@ -37,7 +37,8 @@ class VqbConvDesc(C.Structure):
 
 class VqbWgradDesc(C.Structure):
     _fields_ = [("C", C.c_int32), ("Cout", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("nviews", C.c_int32), ("ntaps", C.c_int32), ("ksplit", C.c_int32), ("dy_view", VqbView),
+                ("nviews", C.c_int32), ("ntaps", C.c_int32), ("ksplit", C.c_int32), ("ld_override", C.c_int64),
+                ("col_offset", C.c_int64), ("dy_view", VqbView),
                 ("views", VqbView * VQB_MAX_VIEWS), ("taps", VqbTap * VQB_MAX_TAPS)]
 
 
@@ -84,6 +85,8 @@ def load():
         "vqb_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "vqb_set_debug_mode": (i32, [i32]),
         "vqb_vq_argmin": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "vqb_pack_weights_fold": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+        "vqb_wgrad_reduce_fold": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name, None)

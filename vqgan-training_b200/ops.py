@@ -38,8 +38,9 @@ def tapmap_tensor(tapmap, device) -> torch.Tensor:
     return t
 
 
-def pack_weights(weight: torch.Tensor, tapmap, transpose: bool, Kpad: int) -> torch.Tensor:
-    """OIHW fp32 -> bf16 [R][len(tapmap)][Kpad] (R = Cin if transpose else Cout)."""
+def pack_weights(weight: torch.Tensor, tapmap, transpose: bool, Kpad: int, fold: bool = False) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [R][len(tapmap)][Kpad] (R = Cin if transpose else Cout). fold: tapmap holds bit masks of taps
+    whose weights are summed (fp32) before the single bf16 rounding."""
     Cout, Cin, KH, KW = weight.shape
     R = Cin if transpose else Cout
     out = torch.empty(R, len(tapmap), Kpad, device=weight.device, dtype=torch.bfloat16)
@@ -47,8 +48,9 @@ def pack_weights(weight: torch.Tensor, tapmap, transpose: bool, Kpad: int) -> to
     w = weight.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    check(_L().vqb_pack_weights(ptr(w), ptr(out), Cout, Cin, KH * KW, len(tapmap), ptr(tm), 1 if transpose else 0,
-                                Kpad, stream_ptr()), "pack_weights")
+    fn = _L().vqb_pack_weights_fold if fold else _L().vqb_pack_weights
+    check(fn(ptr(w), ptr(out), Cout, Cin, KH * KW, len(tapmap), ptr(tm), 1 if transpose else 0, Kpad, stream_ptr()),
+          "pack_weights")
     return out
 
 
@@ -67,11 +69,11 @@ class PackedCache:
             self._geoms[key] = g
         return g
 
-    def get(self, weight: torch.Tensor, key, tapmap, transpose, Kpad):
+    def get(self, weight: torch.Tensor, key, tapmap, transpose, Kpad, fold=False):
         ver = (weight._version, weight.data_ptr())
         ent = self._store.get(key)
         if ent is None or ent[0] != ver:
-            ent = (ver, pack_weights(weight, tapmap, transpose, Kpad))
+            ent = (ver, pack_weights(weight, tapmap, transpose, Kpad, fold))
             self._store[key] = ent
         return ent[1]
 
@@ -316,6 +318,78 @@ def conv(x, weight, bias, cache, kind="s1", residual=None, relu=False, input_is_
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+class UpConvFn(torch.autograd.Function):
+    """Upsample (nearest x2, ae.py:165) + conv3x3 p1 (ae.py:166) without materialising the 4x tensor: four phase convs with
+    2x2 folded taps over the low-res input (4/9 of the MACs). Backward: one 16-tap conv over the
+    four parity views of dy (data gradient) and four phase weight-gradient GEMMs unfolded by vqb_wgrad_reduce_fold."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cache):
+        require_cuda(x)
+        x = x.contiguous()
+        N, h, w, Cp = x.shape
+        Cout, Cin, KH, KW = weight.shape
+        assert KH == 3 and KW == 3 and Cp == plans.cpad(Cin)
+        Cop = plans.cpad(Cout)
+        alloc = torch.empty if Cop == Cout else torch.zeros
+        out = alloc(N, 2 * h, 2 * w, Cop, device=x.device, dtype=torch.bfloat16)
+        b = bias.detach().float() if bias is not None else None
+        strides = (4 * h * w * Cop, 2 * 2 * w * Cop, 2 * Cop, 1)
+        for ph in range(2):
+            for pw in range(2):
+                g = cache.geom(("uf", N, h, w, ph, pw), lambda: plans.geom_up_fwd(N, h, w, Cp, ph, pw))
+                wp = cache.get(weight, ("ufwd", ph, pw), g.tapmask, False, Cp, fold=True)
+                run_conv_gemm(g, x, wp, Cout, out, strides, out_ptr_offset_bytes=(ph * 2 * w + pw) * Cop * 2, bias=b)
+        ctx.save_for_backward(x, weight)
+        ctx.cache, ctx.has_bias = cache, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight = ctx.saved_tensors
+        cache = ctx.cache
+        N, h, w, Cp = x.shape
+        Cout, Cin, KH, KW = weight.shape
+        Cop = plans.cpad(Cout)
+        dy = gout.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gd = cache.geom(("ud", N, h, w), lambda: plans.geom_up_dgrad(N, h, w, Cop))
+            wpd = cache.get(weight, ("udgrad",), gd.tapmask, True, Cop, fold=True)
+            gx_alloc = torch.empty if Cp == Cin else torch.zeros
+            gx = gx_alloc(N, h, w, Cp, device=x.device, dtype=torch.bfloat16)
+            run_conv_gemm(gd, dy, wpd, Cin, gx, plans.nhwc_strides(h, w, Cp))
+        if ctx.needs_input_grad[1]:
+            C64 = ((Cp + 63) // 64) * 64
+            g00 = cache.geom(("uf", N, h, w, 0, 0), lambda: plans.geom_up_fwd(N, h, w, Cp, 0, 0))
+            ksplit = choose_ksplit(g00, Cop)
+            partial = torch.empty(ksplit, Cop, 16 * C64, device=x.device, dtype=torch.float32)
+            masks = []
+            for ph in range(2):
+                for pw in range(2):
+                    g = cache.geom(("uf", N, h, w, ph, pw), lambda: plans.geom_up_fwd(N, h, w, Cp, ph, pw))
+                    dk = ("uwgrad", Cop, ksplit)
+                    descs = g.__dict__.setdefault("_descs", {})
+                    d = descs.get(dk)
+                    if d is None:
+                        d = plans.wgrad_desc(g, Cop, ksplit, dy_view=plans.up_dy_view(N, h, w, Cop, ph, pw),
+                                             ld_override=16 * C64, col_offset=(ph * 2 + pw) * 4 * C64)
+                        descs[dk] = d
+                    check(_L().vqb_wgrad_gemm(d, ptr(dy), ptr(x), ptr(partial), stream_ptr()), "wgrad_gemm(up)")
+                    masks += g.tapmask
+            gw = torch.empty(Cout, Cin, 3, 3, device=x.device, dtype=torch.float32)
+            tm = tapmap_tensor(masks, x.device)
+            check(_L().vqb_wgrad_reduce_fold(ptr(partial), ptr(gw), ksplit, Cout, Cop, Cin, 9, 16, C64, ptr(tm),
+                                             stream_ptr()), "wgrad_reduce_fold")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = colsum(N * 4 * h * w, dy, Cop)[:Cout]
+        return gx, gw, gb, None
+
+
+def upsample_conv(x, weight, bias, cache):
+    return UpConvFn.apply(x, weight, bias, cache)
+
+
 class GroupNormSiLUFn(torch.autograd.Function):
     """FP32GroupNorm (32 groups, eps 1e-6, biased variance, fp32 statistics; ae.py:41-53) fused with swish
     (ae.py:13-14): one statistics pass + one apply pass over bf16 NHWC, instead of cast/GN/cast/sigmoid/mul."""

@@ -32,6 +32,7 @@ class ConvGeom:
     views: List[VqbView] = field(default_factory=list)
     taps: List[Tuple[int, int, int]] = field(default_factory=list)  # (view, dw, dh)
     tapmap: List[int] = field(default_factory=list)
+    tapmask: List[int] = field(default_factory=list)  # folded weights: slot -> bit set of source taps (else empty)
 
 
 def geom_s1(N, H, W, C, k) -> ConvGeom:
@@ -102,6 +103,53 @@ def geom_patch(N, H, W, C, k) -> ConvGeom:
     return g
 
 
+# ---- nearest-2x upsample fused into the 3x3 conv (ae.py:164-167), SURVEY.md Appendix A ------------------------------
+# out[2a+ph, 2b+pw] = sum_{i,j in 0..1} Wf[ph,pw][i][j] . x[a + OFF[ph][i], b + OFF[pw][j]]
+# with Wf[ph,pw][i][j] = sum_{kh in SET[ph][i]} sum_{kw in SET[pw][j]} W[kh,kw]   (4/9 of the MACs, no 4x tensor)
+_UP_OFF = {0: (-1, 0), 1: (0, 1)}
+_UP_SET = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+
+
+def _up_mask(ph, pw, i, j) -> int:
+    m = 0
+    for kh in _UP_SET[ph][i]:
+        for kw in _UP_SET[pw][j]:
+            m |= 1 << (kh * 3 + kw)
+    return m
+
+
+def geom_up_fwd(N, h, w, C, ph, pw) -> ConvGeom:
+    """Phase (ph,pw) of upsample+conv3x3: a 2x2-tap conv over the LOW-RES x writing the (ph,pw) sub-grid of the output."""
+    g = ConvGeom(N, h, w, C, [dense_view(N, h, w, C)])
+    for i in range(2):
+        for j in range(2):
+            g.taps.append((0, _UP_OFF[pw][j], _UP_OFF[ph][i]))
+            g.tapmask.append(_up_mask(ph, pw, i, j))
+    return g
+
+
+def up_dy_view(N, h, w, Cop, ph, pw) -> VqbView:
+    """Parity view (ph,pw) of dy / out [N, 2h, 2w, Cop]."""
+    return VqbView(offset=(ph * 2 * w + pw) * Cop, Wv=w, Hv=h, Nv=N, _pad=0, sw=2 * Cop, sh=2 * 2 * w * Cop,
+                   sn=4 * h * w * Cop)
+
+
+def geom_up_dgrad(N, h, w, Cop) -> ConvGeom:
+    """dx[a,b] = sum over the 4 phases and 2x2 taps of dy_phase[a - dh, b - dw] . Wf^T : one 16-tap conv over the four
+    parity views of dy."""
+    g = ConvGeom(N, h, w, Cop)
+    for ph in range(2):
+        for pw in range(2):
+            g.views.append(up_dy_view(N, h, w, Cop, ph, pw))
+    for ph in range(2):
+        for pw in range(2):
+            for i in range(2):
+                for j in range(2):
+                    g.taps.append((ph * 2 + pw, -_UP_OFF[pw][j], -_UP_OFF[ph][i]))
+                    g.tapmask.append(_up_mask(ph, pw, i, j))
+    return g
+
+
 def conv_desc(g: ConvGeom, Cout: int, out_strides, flags=0, out_f32=False) -> VqbConvDesc:
     """out_strides = (on, oh, ow, oc) in elements."""
     d = VqbConvDesc()
@@ -123,12 +171,13 @@ def nchw_strides(C, H, W):
     return (C * H * W, W, 1, H * W)
 
 
-def wgrad_desc(g: ConvGeom, Cout_pad: int, ksplit: int) -> VqbWgradDesc:
-    """x operand geometry = forward geometry g; dy is the dense (N, Ho, Wo, Cout_pad) tensor."""
+def wgrad_desc(g: ConvGeom, Cout_pad: int, ksplit: int, dy_view=None, ld_override=0, col_offset=0) -> VqbWgradDesc:
+    """x operand geometry = forward geometry g; dy is the dense (N, Ho, Wo, Cout_pad) tensor unless dy_view is given."""
     d = VqbWgradDesc()
     d.C, d.Cout, d.N, d.H, d.W = g.C, Cout_pad, g.N, g.Ho, g.Wo
     d.nviews, d.ntaps, d.ksplit = len(g.views), len(g.taps), ksplit
-    d.dy_view = dense_view(g.N, g.Ho, g.Wo, Cout_pad)
+    d.ld_override, d.col_offset = ld_override, col_offset
+    d.dy_view = dy_view if dy_view is not None else dense_view(g.N, g.Ho, g.Wo, Cout_pad)
     for i, v in enumerate(g.views):
         d.views[i] = v
     for i, (v, dw, dh) in enumerate(g.taps):
