@@ -114,6 +114,12 @@ class FP32GroupNorm(nn.GroupNorm):
         y = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu)
         return _exit(Act(y, a.C), ext)
 
+    def forward_with_skip(self, a: "Act", silu: bool = True):
+        """-> (normalised activation, the input again). Consumers of the second output (the residual path) get their
+        gradient summed inside the GroupNorm backward kernel (no separate accumulation pass)."""
+        y, skip = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu, with_skip=True)
+        return Act(y, a.C), Act(skip, a.C)
+
 
 class AttnBlock(nn.Module):
     def __init__(self, in_channels: int):
@@ -129,7 +135,9 @@ class AttnBlock(nn.Module):
 
     def attention(self, h_) -> Act:
         a, _ = _enter(h_)
-        h = self.norm(a)
+        return self.attention_from_normed(self.norm(a))
+
+    def attention_from_normed(self, h: Act) -> Act:
         qkv = self.qkv.forward_act(h)  # [N,H,W,3C] : q | k | v channel blocks (ae.py:77)
         import attention as attn_core
 
@@ -138,8 +146,9 @@ class AttnBlock(nn.Module):
 
     def forward(self, x):
         a, ext = _enter(x)
-        h = self.attention(a)
-        out = self.proj_out.forward_act(h, residual=a)  # x + proj_out(attn(x)) fused in the conv epilogue
+        hn, a_skip = self.norm.forward_with_skip(a, silu=False)
+        h = self.attention_from_normed(hn)
+        out = self.proj_out.forward_act(h, residual=a_skip)  # x + proj_out(attn(x)) fused in the conv epilogue
         return _exit(out, ext)
 
 
@@ -163,10 +172,10 @@ class ResnetBlock(nn.Module):
 
     def forward(self, x):
         a, ext = _enter(x)
-        h = self.norm1(a, silu=True)
+        h, a_skip = self.norm1.forward_with_skip(a, silu=True)
         h = self.conv1.forward_act(h)
         h = self.norm2(h, silu=True)
-        skip = self.nin_shortcut.forward_act(a) if self.in_channels != self.out_channels else a
+        skip = self.nin_shortcut.forward_act(a_skip) if self.in_channels != self.out_channels else a_skip
         out = self.conv2.forward_act(h, residual=skip)  # x + h fused in conv2's epilogue
         return _exit(out, ext)
 

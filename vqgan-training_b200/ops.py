@@ -392,10 +392,14 @@ def upsample_conv(x, weight, bias, cache):
 
 class GroupNormSiLUFn(torch.autograd.Function):
     """FP32GroupNorm (32 groups, eps 1e-6, biased variance, fp32 statistics; ae.py:41-53) fused with swish
-    (ae.py:13-14): one statistics pass + one apply pass over bf16 NHWC, instead of cast/GN/cast/sigmoid/mul."""
+    (ae.py:13-14): one statistics pass + one apply pass over bf16 NHWC, instead of cast/GN/cast/sigmoid/mul.
+
+    with_skip=True additionally returns the input itself as a second output (the ResnetBlock skip connection): the
+    gradient arriving through that output is summed into dx INSIDE the backward apply kernel instead of by a separate
+    autograd accumulation kernel."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, silu):
+    def forward(ctx, x, gamma, beta, groups, eps, silu, with_skip):
         require_cuda(x)
         x = x.contiguous()
         N, H, W, C = x.shape
@@ -406,26 +410,32 @@ class GroupNormSiLUFn(torch.autograd.Function):
         check(_L().vqb_gn_silu_fwd(ptr(x), ptr(y), ptr(ga), ptr(be), ptr(mr), ptr(ws), N, H * W, C, groups, eps,
                                    1 if silu else 0, stream_ptr()), "gn_silu_fwd")
         ctx.save_for_backward(x, gamma, beta, mr)
-        ctx.groups, ctx.silu = groups, silu
+        ctx.groups, ctx.silu, ctx.with_skip = groups, silu, with_skip
+        ctx.set_materialize_grads(False)  # an unused output arrives as None, not as a zero tensor
+        if with_skip:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gskip=None):
         x, gamma, beta, mr = ctx.saved_tensors
         N, H, W, C = x.shape
+        if gy is None:  # only the skip output was used
+            return (gskip, None, None, None, None, None, None)
         gy = gy.contiguous()
+        add = gskip.contiguous() if gskip is not None else None
         dx = torch.empty_like(x)
         dg = torch.empty(C, device=x.device, dtype=torch.float32)
         db = torch.empty(C, device=x.device, dtype=torch.float32)
         ws = torch.empty(N * C * 2 + N * ctx.groups * 2, device=x.device, dtype=torch.float32)
         ga, be = gamma.detach().float(), beta.detach().float()
-        check(_L().vqb_gn_silu_bwd(ptr(x), ptr(gy), 0, ptr(dx), ptr(ga), ptr(be), ptr(mr), ptr(dg), ptr(db), ptr(ws),
-                                   N, H * W, C, ctx.groups, 1 if ctx.silu else 0, stream_ptr()), "gn_silu_bwd")
-        return dx, dg, db, None, None, None
+        check(_L().vqb_gn_silu_bwd(ptr(x), ptr(gy), ptr(add), ptr(dx), ptr(ga), ptr(be), ptr(mr), ptr(dg), ptr(db),
+                                   ptr(ws), N, H * W, C, ctx.groups, 1 if ctx.silu else 0, stream_ptr()), "gn_silu_bwd")
+        return dx, dg, db, None, None, None, None
 
 
-def group_norm_silu(x, gamma, beta, groups=32, eps=1e-6, silu=True):
-    return GroupNormSiLUFn.apply(x, gamma, beta, groups, eps, silu)
+def group_norm_silu(x, gamma, beta, groups=32, eps=1e-6, silu=True, with_skip=False):
+    return GroupNormSiLUFn.apply(x, gamma, beta, groups, eps, silu, with_skip)
 
 
 class Upsample2xFn(torch.autograd.Function):
