@@ -190,12 +190,14 @@ def profile_conv_kernels(tr, batch_dev):
         rec["conv"].append((e0, e1, flops_conv(g, Cout), ("conv", g.N, g.Ho, g.Wo, g.C, Cout, len(g.taps), len(g.views))))
         return r
 
-    def wgrad_wrap(g, x, dy, weight_shape, Cout_pad):
+    def wgrad_wrap(g, x, dy, weight_shape, Cout_pad, **kk):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = orig_wgrad(g, x, dy, weight_shape, Cout_pad)
+        r = orig_wgrad(g, x, dy, weight_shape, Cout_pad, **kk)
         e1.record()
         Cout, Cin, KH, KW = weight_shape
+        if g.C == 24 and len(g.taps) == 3:  # fat-pixel first layer: 3 real channels x 9 taps, not the padded 24 x 3
+            Cin, KH, KW = 3, 3, 3
         rec["wgrad"].append((e0, e1, 2.0 * g.N * g.Ho * g.Wo * Cout * Cin * KH * KW,
                              ("wgrad", g.N, g.Ho, g.Wo, g.C, Cout, len(g.taps), len(g.views))))
         return r

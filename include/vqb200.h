@@ -99,6 +99,9 @@ typedef struct VqbWgradDesc {
     VqbTap taps[VQB_MAX_TAPS];
 } VqbWgradDesc;
 
+/* 1 if vqb_conv_gemm supports VQB_EPI_STATS for this descriptor (staged epilogue, whole sub-tiles inside one image) */
+int vqb_conv_stats_ok(const VqbConvDesc* d);
+
 int vqb_wgrad_gemm(const VqbWgradDesc* d, const void* dy, const void* x, float* partial, void* stream);
 
 /* number of fp32 columns per Cout row of the wgrad partial buffer: ntaps * roundup(C, 64) */
@@ -135,6 +138,12 @@ int vqb_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp
                      const float* inv_scale, void* stream);
 int vqb_nhwc_to_nchw(const void* g, float* gx, int N, int C, int H, int W, int Cpad, const float* inv_scale,
                      void* stream);
+/* variants that write / read the interior of a zero-framed [N][H+2p][W+2p][Cpad] buffer (first-layer "fat pixel" conv:
+ * three horizontally adjacent 8-channel pixels are one 24-channel K run, 3 taps instead of 9) */
+int vqb_nchw_to_nhwc_pad(const float* x, void* y, int N, int C, int H, int W, int Cpad, int pad, const float* shift,
+                         const float* inv_scale, void* stream);
+int vqb_nhwc_to_nchw_pad(const void* g, float* gx, int N, int C, int H, int W, int Cpad, int pad,
+                         const float* inv_scale, void* stream);
 
 /*
  * FP32GroupNorm (+ swish) forward / backward on bf16 NHWC: 32 groups, biased variance, eps inside the sqrt, fp32
@@ -143,6 +152,9 @@ int vqb_nhwc_to_nchw(const void* g, float* gx, int N, int C, int H, int W, int C
  */
 int vqb_gn_silu_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mr, double* ws, int N,
                     int HW, int C, int G, float eps, int silu, void* stream);
+/* forward when the producing conv already accumulated chsums[N][C][2] (VQB_EPI_STATS): finalise + apply only */
+int vqb_gn_silu_fwd_pre(const void* x, void* y, const float* gamma, const float* beta, float* mr, const float* chsums,
+                        int N, int HW, int C, int G, float eps, int silu, void* stream);
 int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
                     const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
                     void* stream);

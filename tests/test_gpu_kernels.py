@@ -16,6 +16,6 @@ def probe():
     return importlib.import_module("gpu_probe")
 
 
-@pytest.mark.parametrize("group", ["gemm", "conv", "conv2", "wgrad", "elem", "lpips", "up"])
+@pytest.mark.parametrize("group", ["gemm", "conv", "conv2", "wgrad", "elem", "lpips", "up", "stats", "fat"])
 def test_kernel_group(probe, group):
     assert getattr(probe, "group_" + group)(), f"kernel parity group {group} has failures (see stdout)"

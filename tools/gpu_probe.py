@@ -432,6 +432,90 @@ def group_up():
     return ok
 
 
+def group_stats():
+    """GroupNorm statistics accumulated by the conv epilogue (VQB_EPI_STATS) + vqb_gn_silu_fwd_pre vs torch."""
+    import ops
+    ok = True
+    torch.manual_seed(0)
+    for (N, H, W, Ci, Co, res) in [(2, 32, 32, 64, 128, False), (2, 64, 64, 128, 128, True), (1, 32, 32, 512, 512, True),
+                                   (3, 16, 16, 64, 64, False)]:
+        x = rnd(N, H, W, Ci).to(torch.bfloat16)
+        wt = rnd(Co, Ci, 3, 3) * (Ci * 9) ** -0.5
+        b = rnd(Co)
+        r = rnd(N, H, W, Co).to(torch.bfloat16) if res else None
+        cache = ops.PackedCache()
+        out, st = ops.conv(x, wt, b, cache, "s1", residual=r, want_stats=True)
+        torch.cuda.synchronize()
+        tag = f"conv+stats N={N} {H}x{W} {Ci}->{Co} res={res}"
+        if st is None:
+            print("SKIP (stats unsupported)", tag)
+            continue
+        of = out.float()
+        ref = torch.stack([of.sum((1, 2)), (of * of).sum((1, 2))], dim=-1)  # [N, C, 2]
+        ok &= report(tag + " sums", st.reshape(N, -1), ref.reshape(N, -1), tol=1e-4)
+        gamma, beta = rnd(Co) * 0.5 + 1, rnd(Co) * 0.2
+        y = ops.group_norm_silu(out, gamma, beta, 32, 1e-6, True, chsums=st)
+        yr = F.group_norm(of.permute(0, 3, 1, 2), 32, gamma, beta, 1e-6)
+        yr = (yr * torch.sigmoid(yr)).permute(0, 2, 3, 1)
+        ok &= report("   gn_silu via conv-epilogue statistics", y, yr, tol=1e-2)
+    # folded upsample conv accumulates the four phase launches into one statistics tensor
+    x = rnd(2, 16, 16, 128).to(torch.bfloat16)
+    wt = rnd(128, 128, 3, 3) * (128 * 9) ** -0.5
+    out, st = ops.upsample_conv(x, wt, rnd(128), ops.PackedCache(), want_stats=True)
+    torch.cuda.synchronize()
+    if st is not None:
+        of = out.float()
+        ref = torch.stack([of.sum((1, 2)), (of * of).sum((1, 2))], dim=-1)
+        ok &= report("upconv+stats sums", st.reshape(2, -1), ref.reshape(2, -1), tol=1e-4)
+    else:
+        print("SKIP upconv stats unsupported")
+    return ok
+
+
+def group_fat():
+    """first-layer fat-pixel conv (3 taps of 24 over a zero-framed 8-channel image) vs the ordinary 9-tap path and torch."""
+    import ops
+    ok = True
+    print("fat_conv_enabled:", ops.fat_conv_enabled())
+    if not ops.fat_conv_enabled():
+        return True  # the self-check disabled the path; the ordinary kernels are used
+    torch.manual_seed(0)
+    for (N, H, W, Co) in [(2, 32, 32, 64), (1, 64, 48, 128), (3, 20, 20, 64)]:
+        x = (torch.rand(N, 3, H, W, device=dev) - 0.5).requires_grad_(True)
+        wt = ((torch.rand(Co, 3, 3, 3, device=dev) - 0.5) * 0.5).requires_grad_(True)
+        b = rnd(Co).requires_grad_(True)
+        y = ops.conv(ops.to_nhwc(x, None, None, True), wt, b, ops.PackedCache(), "fat3")
+        gy = rnd(N, H, W, Co).to(torch.bfloat16)
+        y.backward(gy)
+        xr = x.detach().to(torch.bfloat16).float().requires_grad_(True)
+        wr = wt.detach().clone().requires_grad_(True)
+        br = b.detach().clone().requires_grad_(True)
+        yr = F.conv2d(xr, wr, br, padding=1)
+        yr.backward(gy.float().permute(0, 3, 1, 2))
+        tag = f"fat3 N={N} {H}x{W} 3->{Co}"
+        ok &= report(tag + " fwd", y, yr.permute(0, 2, 3, 1), tol=1e-2)
+        ok &= report("   dx", x.grad.permute(0, 2, 3, 1), xr.grad.permute(0, 2, 3, 1), tol=1e-2)
+        ok &= report("   dW", wt.grad.reshape(Co, -1), wr.grad.reshape(Co, -1), tol=1e-2)
+        ok &= report("   db", b.grad[None], br.grad[None], tol=1e-2)
+    # tiny-Cout conv with NCHW fp32 output (decoder conv_out): framed dy -> fat data gradient
+    x = rnd(2, 32, 32, 128).to(torch.bfloat16).requires_grad_(True)
+    wt = (rnd(3, 128, 3, 3) * (128 * 9) ** -0.5).requires_grad_(True)
+    b = rnd(3).requires_grad_(True)
+    y = ops.conv(x, wt, b, ops.PackedCache(), "s1", nchw_out=True)
+    gy = rnd(2, 3, 32, 32)
+    y.backward(gy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.detach().clone().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, padding=1)
+    yr.backward(gy)
+    ok &= report("conv_out 128->3 nchw fwd", y.permute(0, 2, 3, 1), yr.permute(0, 2, 3, 1), tol=1e-2)
+    ok &= report("   dx (fat dgrad over framed dy)", x.grad, xr.grad.permute(0, 2, 3, 1), tol=1e-2)
+    ok &= report("   dW", wt.grad.reshape(3, -1), wr.grad.reshape(3, -1), tol=1e-2)
+    ok &= report("   db", b.grad[None], br.grad[None], tol=1e-2)
+    return ok
+
+
 def group_gemm():
     ok = True
     ok &= case_gemm(128, 64, 16)

@@ -47,3 +47,27 @@ if os.environ.get("VQB_PROFILE", "0") == "1":
         tr.step(next(loader)[0])
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+
+    from torch.autograd import DeviceType
+    evs = [e for e in prof.events() if e.device_type == DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    if evs:
+        span = (max(e.time_range.end for e in evs) - evs[0].time_range.start) / 1e3
+        busy, gaps, cur_end = 0.0, [], evs[0].time_range.start
+        for e in evs:
+            s0, s1 = e.time_range.start, e.time_range.end
+            if s0 > cur_end:
+                gaps.append((s0 - cur_end, e.name))
+                cur_end = s0
+            if s1 > cur_end:
+                busy += s1 - cur_end
+                cur_end = s1
+        print(f"GPU span {span:.2f} ms, busy {busy / 1e3:.2f} ms, idle {span - busy / 1e3:.2f} ms in {len(gaps)} gaps; "
+              f"gaps > 5us: {sum(1 for g in gaps if g[0] > 5)} totalling {sum(g[0] for g in gaps if g[0] > 5) / 1e3:.2f} ms")
+        from collections import Counter
+        c = Counter()
+        for g, name in gaps:
+            if g > 5:
+                c[name[:60]] += g
+        for name, g in c.most_common(15):
+            print(f"   idle before {name}: {g / 1e3:.2f} ms")

@@ -40,11 +40,13 @@ from utils import wavelet_transform_multi_channel
 class Act:
     """Internal activation: bf16 NHWC tensor `t` [N,H,W,Cp] carrying its true channel count `C`."""
 
-    __slots__ = ("t", "C")
+    __slots__ = ("t", "C", "stats", "framed")
 
-    def __init__(self, t: Tensor, C: int):
+    def __init__(self, t: Tensor, C: int, stats=None, framed=False):
         self.t = t
         self.C = C
+        self.stats = stats  # per-(n, channel) sum / sum of squares [N, C, 2] when the producing conv computed them
+        self.framed = framed  # t is a zero-framed [N, H+2, W+2, 8] image (input of a "fat pixel" first-layer conv)
 
     @property
     def shape(self):  # reference-style (N, C, H, W)
@@ -87,11 +89,17 @@ class StandardizedC2d(nn.Conv2d):
             return "patch"
         raise NotImplementedError(f"conv k={k} s={s} p={p} is not on the hot path")
 
-    def forward_act(self, a: Act, residual: Act = None, relu=False, input_is_relu=False, nchw_out=False):
-        out = ops.conv(a.t, self.weight, self.bias, self._packed, self._kind(),
-                       residual.t if residual is not None else None, relu, input_is_relu, nchw_out)
+    def forward_act(self, a: Act, residual: Act = None, relu=False, input_is_relu=False, nchw_out=False,
+                    want_stats=False):
+        """want_stats: also accumulate the GroupNorm statistics of the output in the conv epilogue (Act.stats)."""
+        want_stats = want_stats and not nchw_out and os.environ.get("VQB_GN_STATS_FUSION", "1") == "1"
+        kind = "fat3" if a.framed else self._kind()
+        out = ops.conv(a.t, self.weight, self.bias, self._packed, kind,
+                       residual.t if residual is not None else None, relu, input_is_relu, nchw_out, want_stats)
         if nchw_out:
             return out
+        if want_stats:
+            return Act(out[0], self.out_channels, out[1])
         return Act(out, self.out_channels)
 
     def forward(self, x):
@@ -111,13 +119,14 @@ class FP32GroupNorm(nn.GroupNorm):
 
     def forward(self, input, silu: bool = False):
         a, ext = _enter(input)
-        y = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu)
+        y = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu, chsums=a.stats)
         return _exit(Act(y, a.C), ext)
 
     def forward_with_skip(self, a: "Act", silu: bool = True):
         """-> (normalised activation, the input again). Consumers of the second output (the residual path) get their
         gradient summed inside the GroupNorm backward kernel (no separate accumulation pass)."""
-        y, skip = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu, with_skip=True)
+        y, skip = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu, with_skip=True,
+                                      chsums=a.stats)
         return Act(y, a.C), Act(skip, a.C)
 
 
@@ -173,10 +182,10 @@ class ResnetBlock(nn.Module):
     def forward(self, x):
         a, ext = _enter(x)
         h, a_skip = self.norm1.forward_with_skip(a, silu=True)
-        h = self.conv1.forward_act(h)
+        h = self.conv1.forward_act(h, want_stats=True)  # norm2's statistics come out of conv1's epilogue
         h = self.norm2(h, silu=True)
         skip = self.nin_shortcut.forward_act(a_skip) if self.in_channels != self.out_channels else a_skip
-        out = self.conv2.forward_act(h, residual=skip)  # x + h fused in conv2's epilogue
+        out = self.conv2.forward_act(h, residual=skip, want_stats=True)  # x + h fused in conv2's epilogue
         return _exit(out, ext)
 
 
@@ -188,7 +197,7 @@ class Downsample(nn.Module):
     def forward(self, x):
         # F.pad(x, (0,1,0,1)) + stride-2 conv (ae.py:150-154): the pad row/column is the TMA unit's zero fill
         a, ext = _enter(x)
-        return _exit(self.conv.forward_act(a), ext)
+        return _exit(self.conv.forward_act(a, want_stats=True), ext)
 
 
 class Upsample(nn.Module):
@@ -201,10 +210,13 @@ class Upsample(nn.Module):
         # VQB_UPSAMPLE_FOLD=0 selects the literal form (copy kernel + conv), kept for A/B measurements
         a, ext = _enter(x)
         if os.environ.get("VQB_UPSAMPLE_FOLD", "1") == "1":
-            y = ops.upsample_conv(a.t, self.conv.weight, self.conv.bias, self.conv._packed)
+            fuse = os.environ.get("VQB_GN_STATS_FUSION", "1") == "1"
+            y = ops.upsample_conv(a.t, self.conv.weight, self.conv.bias, self.conv._packed, want_stats=fuse)
+            if fuse:
+                return _exit(Act(y[0], self.conv.out_channels, y[1]), ext)
             return _exit(Act(y, self.conv.out_channels), ext)
         up = Act(ops.upsample2x(a.t), a.C)
-        return _exit(self.conv.forward_act(up), ext)
+        return _exit(self.conv.forward_act(up, want_stats=True), ext)
 
 
 class Encoder(nn.Module):
@@ -268,8 +280,9 @@ class Encoder(nn.Module):
 
     def forward(self, x) -> Tensor:
         h = self.wavelet_transform(x)
-        a = Act(ops.to_nhwc(h), h.shape[1])
-        a = self.conv_in.forward_act(a)
+        fat = h.shape[1] <= 8 and ops.fat_conv_enabled()  # RGB input: 3 fat taps of 24 instead of 9 taps of 8 channels
+        a = Act(ops.to_nhwc(h, frame=fat), h.shape[1], framed=fat)
+        a = self.conv_in.forward_act(a, want_stats=True)
         for i_level in range(self.num_resolutions):
             for i_block in range(self.num_res_blocks):
                 a = self.down[i_level].block[i_block](a)
@@ -339,7 +352,7 @@ class Decoder(nn.Module):
 
     def forward(self, z) -> Tensor:
         a = Act(ops.to_nhwc(z), z.shape[1])
-        a = self.conv_in.forward_act(a)
+        a = self.conv_in.forward_act(a, want_stats=True)
         a = self.mid.block_1(a)
         if not isinstance(self.mid.attn_1, nn.Identity):
             a = self.mid.attn_1(a)

@@ -38,7 +38,7 @@ struct alignas(64) ConvParams {
     int32_t n_tiles, total_tiles;
     int32_t block_n, stages, tmem_cols;
     int32_t mtiles, nbuf;
-    int32_t tma_store, mt_dh, mt_dn, _pad1;  // TMA-store epilogue enabled; box offset of the second sub-tile  // 128-row accumulator sub-tiles per CTA tile (1|2); TMEM accumulator buffers (2..4)
+    int32_t tma_store, mt_dh, mt_dn, do_stats;  // TMA-store epilogue enabled; box offset of the second sub-tile  // 128-row accumulator sub-tiles per CTA tile (1|2); TMEM accumulator buffers (2..4)
     int32_t flags, out_f32;
     int32_t dbg, _pad0;
     int64_t on, oh, ow, oc;
@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint8_t* sA = base;
     uint8_t* sB = base + stages * a_bytes;
     uint8_t* sOut = sB + stages * b_bytes;  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
-    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (p.tma_store ? 2 * 16384 : 0));
+    float* sStat = reinterpret_cast<float*>(sOut + 2 * 16384);  // [4 warps][64 ch][2] (GroupNorm statistics combine)
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (p.tma_store ? 2 * 16384 + 2048 : 0));
     uint64_t* empty = full + stages;
     uint64_t* tfull = empty + stages;
     uint64_t* tempty = tfull + 4;
@@ -322,6 +323,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         tma_store_4d(&p.omap, sbuf, col0 + cg * 64, ow0, oh0, on0);
                         bulk_commit();
                     }
+                    if (p.do_stats) {
+                        // GroupNorm statistics of the tile that was just staged (the bf16 values the consumer will read):
+                        // lane l sums channels 2l, 2l+1 of this 64-channel group over the warp's 32 rows (conflict-free
+                        // 32-bit reads of the swizzled rows), the 4 warps are combined through smem, then 128 fp32 atomics.
+                        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+                        const uint32_t jc = lane >> 2, wd = (lane & 3u) << 2;
+#pragma unroll 8
+                        for (uint32_t rr = 0; rr < 32; ++rr) {
+                            const uint32_t row = ew * 32 + rr;
+                            const uint32_t u = *reinterpret_cast<const uint32_t*>(sbuf + row * 128u + (((jc ^ (row & 7u)) << 4) | wd));
+                            const float2 xy = unpack_bf16x2(u);
+                            s0 += xy.x;
+                            q0 = fmaf(xy.x, xy.x, q0);
+                            s1 += xy.y;
+                            q1 = fmaf(xy.y, xy.y, q1);
+                        }
+                        float4* sc = reinterpret_cast<float4*>(sStat + (ew * 64 + 2 * lane) * 2);
+                        *sc = make_float4(s0, q0, s1, q1);
+                        named_bar_sync(2, 128);
+                        const uint32_t t = ew * 32 + lane;  // 0..127 -> (channel t/2, stat t&1)
+                        const int c = cg * 64 + static_cast<int>(t >> 1);
+                        if (col0 + c < p.Cout) {
+                            const float v = sStat[t] + sStat[128 + t] + sStat[256 + t] + sStat[384 + t];
+                            atomicAdd(p.stats + (static_cast<int64_t>(on0) * p.Cout + col0 + c) * 2 + (t & 1u), v);
+                        }
+                        named_bar_sync(2, 128);  // sStat is reused by the next group
+                    }
                     ++obuf;
                 }
             } else
@@ -439,8 +467,27 @@ static int fill_views(const VqbView* views, int nviews, const void* a, int C, in
 
 using namespace vqb;
 
+static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias, const void* res,
+                          const void* mask, void* out, float* stats, void* stream, bool query_only);
+
 extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias,
                              const void* res, const void* mask, void* out, float* stats, void* stream) {
+    return conv_gemm_impl(d, a, w_packed, bias, res, mask, out, stats, stream, false);
+}
+
+// 1 if vqb_conv_gemm can produce GroupNorm statistics (VQB_EPI_STATS) for this descriptor, else 0.
+extern "C" int vqb_conv_stats_ok(const VqbConvDesc* d) {
+    if (!d) return 0;
+    VqbConvDesc q = *d;
+    q.flags &= ~VQB_EPI_STATS;
+    static const uint64_t dummy_aligned[4] = {0, 0, 0, 0};
+    const void* dp = dummy_aligned;
+    const int r = conv_gemm_impl(&q, dp, dp, nullptr, dp, dp, const_cast<void*>(dp), nullptr, nullptr, true);
+    return r == 1 ? 1 : 0;
+}
+
+static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias, const void* res,
+                          const void* mask, void* out, float* stats, void* stream, bool query_only) {
     VQB_CHECK(d && a && w_packed && out, "vqb_conv_gemm: null pointer");
     VQB_CHECK(d->C > 0 && d->C % 8 == 0, "vqb_conv_gemm: C=%d must be a positive multiple of 8", d->C);
     VQB_CHECK(d->Cout > 0 && d->N > 0 && d->H > 0 && d->W > 0, "vqb_conv_gemm: bad extents");
@@ -450,7 +497,7 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
     if ((d->flags & VQB_EPI_BIAS)) VQB_CHECK(bias != nullptr, "vqb_conv_gemm: VQB_EPI_BIAS without bias");
     if ((d->flags & VQB_EPI_RES)) VQB_CHECK(res != nullptr, "vqb_conv_gemm: VQB_EPI_RES without res");
     if ((d->flags & VQB_EPI_MASK)) VQB_CHECK(mask != nullptr, "vqb_conv_gemm: VQB_EPI_MASK without mask");
-    VQB_CHECK(!(d->flags & VQB_EPI_STATS), "vqb_conv_gemm: VQB_EPI_STATS not implemented yet");
+    if ((d->flags & VQB_EPI_STATS)) VQB_CHECK(stats != nullptr, "vqb_conv_gemm: VQB_EPI_STATS without stats");
     if (d->oc == 1 && !d->out_f32) {
         VQB_CHECK(d->on % 8 == 0 && d->oh % 8 == 0 && d->ow % 8 == 0 &&
                       (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
@@ -458,7 +505,7 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
     }
     for (int t = 0; t < d->ntaps; ++t)
         VQB_CHECK(d->taps[t].view >= 0 && d->taps[t].view < d->nviews, "vqb_conv_gemm: tap %d view out of range", t);
-    if (!device_is_sm100()) return set_error(VQB_ENODEVICE, "vqb_conv_gemm: current device is not sm_100");
+    if (!query_only && !device_is_sm100()) return set_error(VQB_ENODEVICE, "vqb_conv_gemm: current device is not sm_100");
 
     ConvParams p;  // ~2.5 KB, filled per call, passed by value (__grid_constant__) to the kernel
     const int p_dbg = debug_mode();
@@ -520,8 +567,17 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
             p.mt_dh = static_cast<int32_t>(obh);
         }
     }
+    // GroupNorm statistics in the epilogue: staged path only, every 128-row sub-tile inside one image, no ragged tiles
+    const bool stats_ok = tma_store && obn == 1 && (d->W % bw == 0) && (d->H % bh == 0) && (d->Cout % 64 == 0);
+    if (d->flags & VQB_EPI_STATS) {
+        if (!stats_ok)
+            return set_error(VQB_EINVAL, "vqb_conv_gemm: VQB_EPI_STATS unsupported for this shape (N=%d H=%d W=%d Cout=%d)",
+                             d->N, d->H, d->W, d->Cout);
+    }
+    p.do_stats = (d->flags & VQB_EPI_STATS) ? 1 : 0;
+    if (query_only) return stats_ok ? 1 : 0;
     const int stage_bytes = mtiles * kABytes + block_n * kBlockK * 2;
-    int stages = (227 * 1024 - 1280 - (tma_store ? 2 * 16384 : 0)) / stage_bytes;
+    int stages = (227 * 1024 - 1280 - (tma_store ? 2 * 16384 + 2048 : 0)) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
     int nbuf = 512 / block_n;
@@ -573,7 +629,7 @@ extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_
         rc = encode_tmap_bf16(&p.omap, out, 4, dims, str, box, 128);
         if (rc != VQB_OK) return rc;
     }
-    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (tma_store ? 2 * 16384 : 0) + 256;
+    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (tma_store ? 2 * 16384 + 2048 : 0) + 256;
     static bool attr_set = false;
     if (!attr_set) {
         VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -82,14 +82,22 @@ __global__ void pack_weights_fold_kernel(const float* __restrict__ w, __nv_bfloa
 
 // ------------------------------------------------------------------ layout conversion
 // y[n,h,w,c] = (x[n,c,h,w] - shift[c]) * inv_scale[c]   (bf16 NHWC, channels >= C zero)
+// pad > 0: y is [N][H+2pad][W+2pad][Cpad] (pre-zeroed) and only its interior is written (W needed then)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int HW,
-                                    int Cpad, const float* __restrict__ shift, const float* __restrict__ inv_scale) {
+                                    int Cpad, const float* __restrict__ shift, const float* __restrict__ inv_scale,
+                                    int W, int pad) {
     const int64_t total = static_cast<int64_t>(N) * HW;
+    const int H = HW / W;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t n = i / HW, p = i % HW;
         const float* xp = x + n * C * HW + p;
-        __nv_bfloat16* yp = y + i * Cpad;
+        int64_t opix = i;
+        if (pad) {
+            const int h = static_cast<int>(p / W), w = static_cast<int>(p % W);
+            opix = (n * (H + 2 * pad) + h + pad) * (W + 2 * pad) + w + pad;
+        }
+        __nv_bfloat16* yp = y + opix * Cpad;
         for (int c0 = 0; c0 < Cpad; c0 += 8) {
             float f[8];
 #pragma unroll
@@ -109,12 +117,18 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 
 // gx[n,c,h,w] = g[n,h,w,c] * inv_scale[c]   (fp32 NCHW out)
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ gx, int N, int C, int HW,
-                                    int Cpad, const float* __restrict__ inv_scale) {
+                                    int Cpad, const float* __restrict__ inv_scale, int W, int pad) {
     const int64_t total = static_cast<int64_t>(N) * HW;
+    const int H = HW / W;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t n = i / HW, p = i % HW;
-        const __nv_bfloat16* gp = g + i * Cpad;
+        int64_t ipix = i;
+        if (pad) {
+            const int h = static_cast<int>(p / W), w = static_cast<int>(p % W);
+            ipix = (n * (H + 2 * pad) + h + pad) * (W + 2 * pad) + w + pad;
+        }
+        const __nv_bfloat16* gp = g + ipix * Cpad;
         float* xp = gx + n * C * HW + p;
         for (int c = 0; c < C; ++c) {
             float v = __bfloat162float(gp[c]);
@@ -187,6 +201,25 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __res
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
         s += sums[(static_cast<int64_t>(n) * C + c) * 2];
         q += sums[(static_cast<int64_t>(n) * C + c) * 2 + 1];
+    }
+    const double m = static_cast<double>(cpg) * HW;
+    const double mean = s / m;
+    double var = q / m - mean * mean;
+    if (var < 0) var = 0;
+    mr[i * 2] = static_cast<float>(mean);
+    mr[i * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// same, from per-channel fp32 sums accumulated by the producing convolution's epilogue (VQB_EPI_STATS)
+__global__ void gn_finalize_f32_kernel(const float* __restrict__ sums, float* __restrict__ mr, int N, int C, int G,
+                                       int HW, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * G) return;
+    const int n = i / G, g = i % G, cpg = C / G;
+    double s = 0, q = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        s += static_cast<double>(sums[(static_cast<int64_t>(n) * C + c) * 2]);
+        q += static_cast<double>(sums[(static_cast<int64_t>(n) * C + c) * 2 + 1]);
     }
     const double m = static_cast<double>(cpg) * HW;
     const double mean = s / m;
@@ -614,7 +647,31 @@ int vqb_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cp
     VQB_CHECK(x && y && Cpad % 8 == 0 && Cpad >= C, "vqb_nchw_to_nhwc: bad arguments");
     const int64_t total = static_cast<int64_t>(N) * H * W;
     nchw_to_nhwc_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, static_cast<__nv_bfloat16*>(y), N, C, H * W, Cpad, shift, inv_scale);
+        x, static_cast<__nv_bfloat16*>(y), N, C, H * W, Cpad, shift, inv_scale, W, 0);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+// Same, into the interior of a PRE-ZEROED [N][H+2pad][W+2pad][Cpad] buffer (zero frame for the "fat pixel" first-layer conv)
+int vqb_nchw_to_nhwc_pad(const float* x, void* y, int N, int C, int H, int W, int Cpad, int pad, const float* shift,
+                         const float* inv_scale, void* stream) {
+    VQB_CHECK(x && y && Cpad % 8 == 0 && Cpad >= C && pad >= 0, "vqb_nchw_to_nhwc_pad: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * H * W;
+    nchw_to_nhwc_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<__nv_bfloat16*>(y), N, C, H * W, Cpad, shift, inv_scale, W, pad);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+// inverse: reads the interior of a padded NHWC buffer
+int vqb_nhwc_to_nchw_pad(const void* g, float* gx, int N, int C, int H, int W, int Cpad, int pad,
+                         const float* inv_scale, void* stream) {
+    VQB_CHECK(g && gx && Cpad % 8 == 0 && Cpad >= C && pad >= 0, "vqb_nhwc_to_nchw_pad: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * H * W;
+    nhwc_to_nchw_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(g), gx, N, C, H * W, Cpad, inv_scale, W, pad);
     VQB_CUDA(cudaGetLastError());
     count_launch();
     return VQB_OK;
@@ -625,7 +682,7 @@ int vqb_nhwc_to_nchw(const void* g, float* gx, int N, int C, int H, int W, int C
     VQB_CHECK(g && gx && Cpad % 8 == 0 && Cpad >= C, "vqb_nhwc_to_nchw: bad arguments");
     const int64_t total = static_cast<int64_t>(N) * H * W;
     nhwc_to_nchw_kernel<<<gs_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(g), gx, N, C, H * W, Cpad, inv_scale);
+        static_cast<const __nv_bfloat16*>(g), gx, N, C, H * W, Cpad, inv_scale, W, 0);
     VQB_CUDA(cudaGetLastError());
     count_launch();
     return VQB_OK;
@@ -650,6 +707,25 @@ int vqb_gn_silu_fwd(const void* x, void* y, const float* gamma, const float* bet
                                                    silu);
     VQB_CUDA(cudaGetLastError());
     count_launch(3);
+    return VQB_OK;
+}
+
+// GroupNorm(+SiLU) forward when the per-(n, channel) sums [N][C][2] (sum, sum of squares; fp32) were already produced by
+// the convolution that wrote x (vqb_conv_gemm with VQB_EPI_STATS): finalise + one apply pass, no statistics pass.
+int vqb_gn_silu_fwd_pre(const void* x, void* y, const float* gamma, const float* beta, float* mr, const float* chsums,
+                        int N, int HW, int C, int G, float eps, int silu, void* stream) {
+    VQB_CHECK(x && y && gamma && beta && mr && chsums, "vqb_gn_silu_fwd_pre: null pointer");
+    VQB_CHECK(C % 8 == 0 && C % G == 0 && C <= 2048, "vqb_gn_silu_fwd_pre: C=%d G=%d unsupported", C, G);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    gn_finalize_f32_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(chsums, mr, N, C, G, HW, eps);
+    int chunks, ppc;
+    const int T = cv_threads(C);
+    cv_grid(HW, C, N, gn_apply_kernel, 0, chunks, ppc);
+    gn_apply_kernel<<<dim3(chunks, N), T, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                   static_cast<__nv_bfloat16*>(y), mr, gamma, beta, HW, C, G, ppc,
+                                                   silu);
+    VQB_CUDA(cudaGetLastError());
+    count_launch(2);
     return VQB_OK;
 }
 

@@ -98,9 +98,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
             const int co0 = m_tile * kWM * p.mtiles;
             const int colbase = n_tile * p.block_n;
             const int nkb = kb1 - kb0;
-            const int rot = (nkb > 0 && !(p.dbg & 4)) ? static_cast<int>((blockIdx.x * 37u) % static_cast<uint32_t>(nkb)) : 0;
+            // no rotation by default: CTAs working on the same pixel split stream the same x / dy boxes in lock-step, so each
+            // box is fetched from HBM once and hit in L2 by the other tiles (a per-CTA rotated start destroys that reuse)
+            const int rot = (nkb > 0 && (p.dbg & 4)) ? static_cast<int>((blockIdx.x * 37u) % static_cast<uint32_t>(nkb)) : 0;
             for (int kbi = 0; kbi < nkb; ++kbi) {
-                // rotated start: lock-stepped CTAs of the same split must not stream the same pixel boxes together
                 int kb = kb0 + kbi + rot;
                 if (kb >= kb1) kb -= nkb;
                 const int tw = kb % p.tiles_w;

@@ -85,6 +85,10 @@ def load():
         "vqb_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "vqb_set_debug_mode": (i32, [i32]),
         "vqb_vq_argmin": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "vqb_nchw_to_nhwc_pad": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+        "vqb_nhwc_to_nchw_pad": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "vqb_gn_silu_fwd_pre": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
+        "vqb_conv_stats_ok": (i32, [C.POINTER(VqbConvDesc)]),
         "vqb_pack_weights_fold": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
         "vqb_wgrad_reduce_fold": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     }

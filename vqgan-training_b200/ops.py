@@ -121,9 +121,10 @@ def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
 
 
 def run_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: int, out: torch.Tensor, out_strides,
-                  out_ptr_offset_bytes=0, bias=None, res=None, mask=None, relu=False, out_f32=False):
+                  out_ptr_offset_bytes=0, bias=None, res=None, mask=None, relu=False, out_f32=False, stats=None):
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_RES if res is not None else 0) | \
-            (EPI_MASK if mask is not None else 0) | (EPI_RELU if relu else 0)
+            (EPI_MASK if mask is not None else 0) | (EPI_RELU if relu else 0) | \
+            (native.EPI_STATS if stats is not None else 0)
     dk = (Cout, tuple(out_strides), flags, out_f32)
     descs = g.__dict__.setdefault("_descs", {})
     d = descs.get(dk)
@@ -132,25 +133,37 @@ def run_conv_gemm(g: plans.ConvGeom, a: torch.Tensor, wp: torch.Tensor, Cout: in
         descs[dk] = d
     off = out_ptr_offset_bytes
     check(_L().vqb_conv_gemm(d, ptr(a), ptr(wp), ptr(bias), (ptr(res) + off) if res is not None else 0,
-                             (ptr(mask) + off) if mask is not None else 0, ptr(out) + off, 0, stream_ptr()),
+                             (ptr(mask) + off) if mask is not None else 0, ptr(out) + off, ptr(stats), stream_ptr()),
           "conv_gemm")
 
 
-def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape, Cout_pad: int) -> torch.Tensor:
-    """-> OIHW fp32 gradient for a conv whose forward geometry is g."""
+def conv_stats_supported(g: plans.ConvGeom, Cout: int, out_strides) -> bool:
+    """Can the conv epilogue produce the GroupNorm statistics of its output for this geometry? (cached per geometry)"""
+    descs = g.__dict__.setdefault("_descs", {})
+    key = ("stats_ok", Cout, tuple(out_strides))
+    ok = descs.get(key)
+    if ok is None:
+        ok = bool(_L().vqb_conv_stats_ok(plans.conv_desc(g, Cout, out_strides, 0, False)))
+        descs[key] = ok
+    return ok
+
+
+def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape, Cout_pad: int,
+              dy_view=None) -> torch.Tensor:
+    """-> OIHW fp32 gradient for a conv whose forward geometry is g (weight_shape = (Cout, K per tap, taps_h, taps_w))."""
     Cout, Cin, KH, KW = weight_shape
-    wk = ("wgrad", Cout_pad)
+    wk = ("wgrad", Cout_pad, dy_view is not None)
     descs = g.__dict__.setdefault("_descs", {})
     ent = descs.get(wk)
     if ent is None:
         ksplit = choose_ksplit(g, Cout_pad)
-        ent = (ksplit, plans.wgrad_desc(g, Cout_pad, ksplit), _L().vqb_wgrad_cols(len(g.taps), g.C))
+        ent = (ksplit, plans.wgrad_desc(g, Cout_pad, ksplit, dy_view=dy_view), _L().vqb_wgrad_cols(len(g.taps), g.C))
         descs[wk] = ent
     ksplit, d, cols = ent
     partial = torch.empty(ksplit, Cout_pad, cols, device=x.device, dtype=torch.float32)
     check(_L().vqb_wgrad_gemm(d, ptr(dy), ptr(x), ptr(partial), stream_ptr()), "wgrad_gemm")
     grad = torch.empty(Cout, Cin, KH, KW, device=x.device, dtype=torch.float32)
-    tm = tapmap_tensor(g.tapmap, x.device)
+    tm = tapmap_tensor(g.tapmap if len(g.tapmap) == len(g.taps) else list(range(len(g.taps))), x.device)
     check(_L().vqb_wgrad_reduce(ptr(partial), ptr(grad), ksplit, Cout, Cout_pad, Cin, KH * KW, len(g.taps),
                                 cols // len(g.taps), ptr(tm), 0, stream_ptr()), "wgrad_reduce")
     return grad
@@ -168,18 +181,23 @@ class ToNHWC(torch.autograd.Function):
     utils.py:70-71). Backward: NHWC bf16 grad -> NCHW fp32 (* inv_scale)."""
 
     @staticmethod
-    def forward(ctx, x, shift, inv_scale):
+    def forward(ctx, x, shift, inv_scale, frame):
         require_cuda(x)
         x = x.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         N, C, H, W = x.shape
         Cp = plans.cpad(C)
-        y = torch.empty(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
-        check(_L().vqb_nchw_to_nhwc(ptr(x), ptr(y), N, C, H, W, Cp, ptr(shift), ptr(inv_scale), stream_ptr()),
-              "nchw_to_nhwc")
+        if frame:  # zero-framed [N, H+2, W+2, Cp] for the "fat pixel" first-layer conv
+            y = torch.zeros(N, H + 2, W + 2, Cp, device=x.device, dtype=torch.bfloat16)
+            check(_L().vqb_nchw_to_nhwc_pad(ptr(x), ptr(y), N, C, H, W, Cp, 1, ptr(shift), ptr(inv_scale),
+                                            stream_ptr()), "nchw_to_nhwc_pad")
+        else:
+            y = torch.empty(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
+            check(_L().vqb_nchw_to_nhwc(ptr(x), ptr(y), N, C, H, W, Cp, ptr(shift), ptr(inv_scale), stream_ptr()),
+                  "nchw_to_nhwc")
         ctx.shape = (N, C, H, W, Cp)
-        ctx.inv_scale = inv_scale
+        ctx.inv_scale, ctx.frame = inv_scale, frame
         return y
 
     @staticmethod
@@ -187,13 +205,43 @@ class ToNHWC(torch.autograd.Function):
         N, C, H, W, Cp = ctx.shape
         gy = gy.contiguous()
         gx = torch.empty(N, C, H, W, device=gy.device, dtype=torch.float32)
-        check(_L().vqb_nhwc_to_nchw(ptr(gy), ptr(gx), N, C, H, W, Cp, ptr(ctx.inv_scale), stream_ptr()),
-              "nhwc_to_nchw")
-        return gx, None, None
+        if ctx.frame:
+            check(_L().vqb_nhwc_to_nchw_pad(ptr(gy), ptr(gx), N, C, H, W, Cp, 1, ptr(ctx.inv_scale), stream_ptr()),
+                  "nhwc_to_nchw_pad")
+        else:
+            check(_L().vqb_nhwc_to_nchw(ptr(gy), ptr(gx), N, C, H, W, Cp, ptr(ctx.inv_scale), stream_ptr()),
+                  "nhwc_to_nchw")
+        return gx, None, None, None
 
 
-def to_nhwc(x, shift=None, inv_scale=None):
-    return ToNHWC.apply(x, shift, inv_scale)
+_fat_state = {"ok": None}
+
+
+def fat_conv_enabled() -> bool:
+    """One-time self check of the fat-pixel first-layer path (it relies on a TMA map whose pixel stride (16 B) is smaller
+    than its 48-byte inner extent): run a tiny conv both ways; disable the path on any error or mismatch."""
+    import os
+
+    if os.environ.get("VQB_FAT_CONV", "1") != "1":
+        return False
+    if _fat_state["ok"] is None:
+        _fat_state["ok"] = False
+        try:
+            g = torch.Generator(device="cuda").manual_seed(1)
+            x = torch.rand(2, 3, 16, 24, device="cuda", generator=g) - 0.5
+            w = torch.rand(64, 3, 3, 3, device="cuda", generator=g) - 0.5
+            c1, c2 = PackedCache(), PackedCache()
+            a = conv(ToNHWC.apply(x, None, None, False), w, None, c1, "s1")
+            b = conv(ToNHWC.apply(x, None, None, True), w, None, c2, "fat3")
+            torch.cuda.synchronize()
+            _fat_state["ok"] = bool(torch.allclose(a.float(), b.float(), rtol=2e-2, atol=2e-2))
+        except Exception:
+            _fat_state["ok"] = False
+    return _fat_state["ok"]
+
+
+def to_nhwc(x, shift=None, inv_scale=None, frame=False):
+    return ToNHWC.apply(x, shift, inv_scale, frame)
 
 
 class ToNCHW(torch.autograd.Function):
@@ -231,13 +279,17 @@ class ConvFn(torch.autograd.Function):
     epilogue), nchw_out (write fp32 [N,Cout,H,W] directly: encoder z / decoder image)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, cache, kind, relu, input_is_relu, nchw_out):
+    def forward(ctx, x, weight, bias, residual, cache, kind, relu, input_is_relu, nchw_out, want_stats=False):
         require_cuda(x)
         N, H, W, Cp = x.shape
         Cout, Cin, KH, KW = weight.shape
         assert Cp == plans.cpad(Cin), f"conv input has {Cp} channels, weight expects {Cin}"
         x = x.contiguous()
-        if kind == "s1":
+        if kind == "fat3":  # x is the zero-framed [N, H+2, W+2, 8] image
+            assert Cp == 8 and KH == 3
+            H, W = H - 2, W - 2
+            g = cache.geom(("fat", N, H, W), lambda: plans.geom_fat3(N, H, W))
+        elif kind == "s1":
             g = cache.geom(("f", N, H, W), lambda: plans.geom_s1(N, H, W, Cp, KH))
         elif kind == "s2":
             g = cache.geom(("f", N, H, W), lambda: plans.geom_s2(N, H, W, Cp))
@@ -247,6 +299,7 @@ class ConvFn(torch.autograd.Function):
             raise ValueError(kind)
         wp = cache.get(weight, ("fwd", kind), g.tapmap, False, Cp)
         Cop = plans.cpad(Cout)
+        ctx.HW = (H, W)
         b = None
         if bias is not None:
             b = bias.detach()
@@ -259,32 +312,66 @@ class ConvFn(torch.autograd.Function):
             alloc = torch.empty if Cop == Cout else torch.zeros
             out = alloc(N, g.Ho, g.Wo, Cop, device=x.device, dtype=torch.bfloat16)
             res = residual.contiguous() if residual is not None else None
-            run_conv_gemm(g, x, wp, Cout, out, plans.nhwc_strides(g.Ho, g.Wo, Cop), bias=b, res=res, relu=relu)
+            ostr = plans.nhwc_strides(g.Ho, g.Wo, Cop)
+            stats = None
+            if want_stats and Cop == Cout and conv_stats_supported(g, Cout, ostr):
+                stats = torch.zeros(N, Cout, 2, device=x.device, dtype=torch.float32)
+            run_conv_gemm(g, x, wp, Cout, out, ostr, bias=b, res=res, relu=relu, stats=stats)
         ctx.save_for_backward(x, weight)
         ctx.cache, ctx.kind, ctx.g = cache, kind, g
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.input_is_relu, ctx.nchw_out = input_is_relu, nchw_out
+        if want_stats and not nchw_out:
+            if stats is None:
+                stats = torch.empty(0, device=x.device)  # "not available" marker
+            ctx.mark_non_differentiable(stats)
+            return out, stats
         return out
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, _gstats=None):
         x, weight = ctx.saved_tensors
         g, kind, cache = ctx.g, ctx.kind, ctx.cache
-        N, H, W, Cp = x.shape
+        N, _, _, Cp = x.shape
+        H, W = ctx.HW
         Cout, Cin, KH, KW = weight.shape
         Cop = plans.cpad(Cout)
+        dy_framed = False
         if ctx.nchw_out:
             gn = gout.float().contiguous()
-            dy = torch.empty(N, g.Ho, g.Wo, Cop, device=x.device, dtype=torch.bfloat16)
-            check(_L().vqb_nchw_to_nhwc(ptr(gn), ptr(dy), N, Cout, g.Ho, g.Wo, Cop, 0, 0, stream_ptr()), "nchw_to_nhwc")
+            if Cop == 8 and KH == 3 and kind == "s1" and fat_conv_enabled():
+                # tiny-Cout conv (decoder conv_out): keep dy in a zero-framed buffer so that the data gradient runs as a
+                # 3-tap fat-pixel conv (24-wide K runs) instead of 9 taps of 8 channels
+                dy_framed = True
+                dy = torch.zeros(N, g.Ho + 2, g.Wo + 2, Cop, device=x.device, dtype=torch.bfloat16)
+                check(_L().vqb_nchw_to_nhwc_pad(ptr(gn), ptr(dy), N, Cout, g.Ho, g.Wo, Cop, 1, 0, 0, stream_ptr()),
+                      "nchw_to_nhwc_pad")
+            else:
+                dy = torch.empty(N, g.Ho, g.Wo, Cop, device=x.device, dtype=torch.bfloat16)
+                check(_L().vqb_nchw_to_nhwc(ptr(gn), ptr(dy), N, Cout, g.Ho, g.Wo, Cop, 0, 0, stream_ptr()),
+                      "nchw_to_nhwc")
         else:
             dy = gout.contiguous()
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[0]:
             mask = x if ctx.input_is_relu else None
             gx_alloc = torch.empty if Cp == Cin else torch.zeros
-            gx = gx_alloc(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
-            if kind == "s1":
+            if kind == "fat3":  # gradient w.r.t. the framed image: write the interior of a zero-framed buffer
+                gx = torch.zeros(N, H + 2, W + 2, Cp, device=x.device, dtype=torch.bfloat16)
+                gd = cache.geom(("d", N, H, W), lambda: plans.geom_s1_dgrad(N, H, W, Cop, KH))
+                wpd = cache.get(weight, ("dgrad", "s1"), gd.tapmap, True, Cop)
+                run_conv_gemm(gd, dy, wpd, Cin, gx, ((H + 2) * (W + 2) * Cp, (W + 2) * Cp, Cp, 1),
+                              out_ptr_offset_bytes=((W + 2) + 1) * Cp * 2)
+            elif dy_framed:
+                gx = gx_alloc(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
+                gdf = cache.geom(("dfat", N, H, W), lambda: plans.geom_fat3(N, H, W, dgrad=True))
+                wpd = cache.get(weight, ("dgrad", "fat3"), gdf.tapmap, True, Cop)
+                run_conv_gemm(gdf, dy, wpd, Cin, gx, plans.nhwc_strides(H, W, Cp), mask=mask)
+            else:
+                gx = gx_alloc(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
+            if kind == "fat3" or dy_framed:
+                pass
+            elif kind == "s1":
                 gd = cache.geom(("d", N, H, W), lambda: plans.geom_s1_dgrad(N, H, W, Cop, KH))
                 wpd = cache.get(weight, ("dgrad", kind), gd.tapmap, True, Cop)
                 run_conv_gemm(gd, dy, wpd, Cin, gx, plans.nhwc_strides(H, W, Cp), mask=mask)
@@ -305,16 +392,29 @@ class ConvFn(torch.autograd.Function):
                         run_conv_gemm(gd, dy, wpd, Cin, gx, (H * W * Cp, k * W * Cp, k * Cp, 1),
                                       out_ptr_offset_bytes=(kh * W + kw) * Cp * 2, mask=mask)
         if ctx.needs_input_grad[1]:
-            gw = run_wgrad(g, x, dy, weight.shape, Cop)
+            if kind == "fat3":  # [Cout][kw*8 + c][kh] -> OIHW
+                g3 = run_wgrad(g, x, dy, (Cout, 24, 3, 1), Cop)
+                gw = g3.view(Cout, 3, 8, 3)[:, :, :Cin, :].permute(0, 2, 3, 1).contiguous()
+            elif dy_framed:
+                gw = run_wgrad(g, x, dy, weight.shape, Cop,
+                               dy_view=plans.framed_interior_view(N, g.Ho, g.Wo, Cop))
+            else:
+                gw = run_wgrad(g, x, dy, weight.shape, Cop)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = colsum(N * g.Ho * g.Wo, dy, Cop)[:Cout]
+            rows = N * (g.Ho + 2) * (g.Wo + 2) if dy_framed else N * g.Ho * g.Wo  # the zero frame adds nothing
+            gb = colsum(rows, dy, Cop)[:Cout]
         if ctx.has_res and ctx.needs_input_grad[3]:
             gres = dy
-        return gx, gw, gb, gres, None, None, None, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None
 
 
-def conv(x, weight, bias, cache, kind="s1", residual=None, relu=False, input_is_relu=False, nchw_out=False):
-    return ConvFn.apply(x, weight, bias, residual, cache, kind, relu, input_is_relu, nchw_out)
+def conv(x, weight, bias, cache, kind="s1", residual=None, relu=False, input_is_relu=False, nchw_out=False,
+         want_stats=False):
+    """-> out, or (out, stats) when want_stats (stats is None if the epilogue cannot produce them for this shape)."""
+    if want_stats and not nchw_out:
+        out, st = ConvFn.apply(x, weight, bias, residual, cache, kind, relu, input_is_relu, nchw_out, True)
+        return out, (st if st.numel() > 0 else None)
+    return ConvFn.apply(x, weight, bias, residual, cache, kind, relu, input_is_relu, nchw_out, False)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -324,7 +424,7 @@ class UpConvFn(torch.autograd.Function):
     four parity views of dy (data gradient) and four phase weight-gradient GEMMs unfolded by vqb_wgrad_reduce_fold."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache):
+    def forward(ctx, x, weight, bias, cache, want_stats=False):
         require_cuda(x)
         x = x.contiguous()
         N, h, w, Cp = x.shape
@@ -335,17 +435,27 @@ class UpConvFn(torch.autograd.Function):
         out = alloc(N, 2 * h, 2 * w, Cop, device=x.device, dtype=torch.bfloat16)
         b = bias.detach().float() if bias is not None else None
         strides = (4 * h * w * Cop, 2 * 2 * w * Cop, 2 * Cop, 1)
+        stats = None
+        g00 = cache.geom(("uf", N, h, w, 0, 0), lambda: plans.geom_up_fwd(N, h, w, Cp, 0, 0))
+        if want_stats and Cop == Cout and conv_stats_supported(g00, Cout, strides):
+            stats = torch.zeros(N, Cout, 2, device=x.device, dtype=torch.float32)  # the 4 phase launches accumulate
         for ph in range(2):
             for pw in range(2):
                 g = cache.geom(("uf", N, h, w, ph, pw), lambda: plans.geom_up_fwd(N, h, w, Cp, ph, pw))
                 wp = cache.get(weight, ("ufwd", ph, pw), g.tapmask, False, Cp, fold=True)
-                run_conv_gemm(g, x, wp, Cout, out, strides, out_ptr_offset_bytes=(ph * 2 * w + pw) * Cop * 2, bias=b)
+                run_conv_gemm(g, x, wp, Cout, out, strides, out_ptr_offset_bytes=(ph * 2 * w + pw) * Cop * 2, bias=b,
+                              stats=stats)
         ctx.save_for_backward(x, weight)
         ctx.cache, ctx.has_bias = cache, bias is not None
+        if want_stats:
+            if stats is None:
+                stats = torch.empty(0, device=x.device)
+            ctx.mark_non_differentiable(stats)
+            return out, stats
         return out
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, _gstats=None):
         x, weight = ctx.saved_tensors
         cache = ctx.cache
         N, h, w, Cp = x.shape
@@ -383,11 +493,14 @@ class UpConvFn(torch.autograd.Function):
                                              stream_ptr()), "wgrad_reduce_fold")
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(N * 4 * h * w, dy, Cop)[:Cout]
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def upsample_conv(x, weight, bias, cache):
-    return UpConvFn.apply(x, weight, bias, cache)
+def upsample_conv(x, weight, bias, cache, want_stats=False):
+    if want_stats:
+        out, st = UpConvFn.apply(x, weight, bias, cache, True)
+        return out, (st if st.numel() > 0 else None)
+    return UpConvFn.apply(x, weight, bias, cache, False)
 
 
 class GroupNormSiLUFn(torch.autograd.Function):
@@ -399,16 +512,20 @@ class GroupNormSiLUFn(torch.autograd.Function):
     autograd accumulation kernel."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, silu, with_skip):
+    def forward(ctx, x, gamma, beta, groups, eps, silu, with_skip, chsums=None):
         require_cuda(x)
         x = x.contiguous()
         N, H, W, C = x.shape
         y = torch.empty_like(x)
         mr = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
-        ws = torch.empty(N * C * 2, device=x.device, dtype=torch.float64)
         ga, be = gamma.detach().float(), beta.detach().float()
-        check(_L().vqb_gn_silu_fwd(ptr(x), ptr(y), ptr(ga), ptr(be), ptr(mr), ptr(ws), N, H * W, C, groups, eps,
-                                   1 if silu else 0, stream_ptr()), "gn_silu_fwd")
+        if chsums is not None:  # statistics were accumulated by the epilogue of the conv that produced x
+            check(_L().vqb_gn_silu_fwd_pre(ptr(x), ptr(y), ptr(ga), ptr(be), ptr(mr), ptr(chsums), N, H * W, C, groups,
+                                           eps, 1 if silu else 0, stream_ptr()), "gn_silu_fwd_pre")
+        else:
+            ws = torch.empty(N * C * 2, device=x.device, dtype=torch.float64)
+            check(_L().vqb_gn_silu_fwd(ptr(x), ptr(y), ptr(ga), ptr(be), ptr(mr), ptr(ws), N, H * W, C, groups, eps,
+                                       1 if silu else 0, stream_ptr()), "gn_silu_fwd")
         ctx.save_for_backward(x, gamma, beta, mr)
         ctx.groups, ctx.silu, ctx.with_skip = groups, silu, with_skip
         ctx.set_materialize_grads(False)  # an unused output arrives as None, not as a zero tensor
@@ -421,7 +538,7 @@ class GroupNormSiLUFn(torch.autograd.Function):
         x, gamma, beta, mr = ctx.saved_tensors
         N, H, W, C = x.shape
         if gy is None:  # only the skip output was used
-            return (gskip, None, None, None, None, None, None)
+            return (gskip, None, None, None, None, None, None, None)
         gy = gy.contiguous()
         add = gskip.contiguous() if gskip is not None else None
         dx = torch.empty_like(x)
@@ -431,11 +548,11 @@ class GroupNormSiLUFn(torch.autograd.Function):
         ga, be = gamma.detach().float(), beta.detach().float()
         check(_L().vqb_gn_silu_bwd(ptr(x), ptr(gy), ptr(add), ptr(dx), ptr(ga), ptr(be), ptr(mr), ptr(dg), ptr(db),
                                    ptr(ws), N, H * W, C, ctx.groups, 1 if ctx.silu else 0, stream_ptr()), "gn_silu_bwd")
-        return dx, dg, db, None, None, None, None
+        return dx, dg, db, None, None, None, None, None
 
 
-def group_norm_silu(x, gamma, beta, groups=32, eps=1e-6, silu=True, with_skip=False):
-    return GroupNormSiLUFn.apply(x, gamma, beta, groups, eps, silu, with_skip)
+def group_norm_silu(x, gamma, beta, groups=32, eps=1e-6, silu=True, with_skip=False, chsums=None):
+    return GroupNormSiLUFn.apply(x, gamma, beta, groups, eps, silu, with_skip, chsums)
 
 
 class Upsample2xFn(torch.autograd.Function):

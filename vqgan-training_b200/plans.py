@@ -150,6 +150,28 @@ def geom_up_dgrad(N, h, w, Cop) -> ConvGeom:
     return g
 
 
+# ---- first-layer "fat pixel" 3x3 conv over an 8-channel image ------------------------------------------------------
+# The image lives in a zero-framed buffer [N][H+2][W+2][8]; three horizontally adjacent pixels are 24 CONTIGUOUS elements,
+# so the conv becomes 3 taps (kh) of K = 24 instead of 9 taps of K = 8: a third of the TMA requests on a layer that is
+# purely TMA-request bound (K = 8 real channels per 128-byte row). Weights [Cout][kh][kw*8 + c] are the ordinary
+# [Cout][9][8] packing read with a different stride.
+def fat_view(N, H, W) -> VqbView:
+    return VqbView(offset=0, Wv=W, Hv=H + 2, Nv=N, _pad=0, sw=8, sh=(W + 2) * 8, sn=(H + 2) * (W + 2) * 8)
+
+
+def geom_fat3(N, H, W, dgrad=False) -> ConvGeom:
+    g = ConvGeom(N, H, W, 24, [fat_view(N, H, W)])
+    for kh in range(3):
+        g.taps.append((0, 0, kh))
+    g.tapmap = [8 - t for t in range(9)] if dgrad else list(range(9))  # 9 packed slots of 8 = 3 fat taps of 24
+    return g
+
+
+def framed_interior_view(N, H, W, C) -> VqbView:
+    """The dense (N, H, W) grid seen inside a zero-framed [N][H+2][W+2][C] buffer."""
+    return VqbView(offset=((W + 2) + 1) * C, Wv=W, Hv=H, Nv=N, _pad=0, sw=C, sh=(W + 2) * C, sn=(H + 2) * (W + 2) * C)
+
+
 def conv_desc(g: ConvGeom, Cout: int, out_strides, flags=0, out_f32=False) -> VqbConvDesc:
     """out_strides = (on, oh, ow, oc) in elements."""
     d = VqbConvDesc()

@@ -110,9 +110,10 @@ class LPIPS(nn.Module):
 
         # NOTE: the reference leaves this module in train mode, so its nn.Dropout(0.5) in front of
         # every lin layer is active during training. The fused tail implements eval-mode semantics.
-        a0 = Act(self.scaling_layer.to_act(input), 3)
+        fat = ops.fat_conv_enabled()
+        a0 = Act(self.scaling_layer.to_act(input, fat), 3, framed=fat)
         with torch.no_grad():
-            a1 = Act(self.scaling_layer.to_act(target), 3)
+            a1 = Act(self.scaling_layer.to_act(target, fat), 3, framed=fat)
             outs1 = self.net.forward_acts(a1)
         outs0 = self.net.forward_acts(a0)
         lins = [self.lin0, self.lin1, self.lin2, self.lin3, self.lin4]
@@ -132,11 +133,12 @@ class ScalingLayer(nn.Module):
     def forward(self, inp):
         return (inp - self.shift) / self.scale
 
-    def to_act(self, inp):
-        """(inp - shift) / scale fused into the NCHW fp32 -> NHWC bf16 layout kernel."""
+    def to_act(self, inp, frame=False):
+        """(inp - shift) / scale fused into the NCHW fp32 -> NHWC bf16 layout kernel (optionally zero-framed for the
+        fat-pixel first VGG conv)."""
         shift = self.shift.reshape(-1).float().contiguous()
         inv = (1.0 / self.scale.reshape(-1).float()).contiguous()
-        return ops.to_nhwc(inp, shift, inv)
+        return ops.to_nhwc(inp, shift, inv, frame)
 
 
 class NetLinLayer(nn.Module):
@@ -257,7 +259,8 @@ class PatchDiscriminator(nn.Module):
     def forward(self, x):
         from ae import Act
 
-        a = Act(self.scaling_layer.to_act(x), 3)
+        fat = ops.fat_conv_enabled()
+        a = Act(self.scaling_layer.to_act(x, fat), 3, framed=fat)
         f1 = _run_trunk_slice(self.slice1[0], a, False)
         f2 = _run_trunk_slice(self.slice2[0], f1, False)
         f3 = _run_trunk_slice(self.slice3[0], f2, False)
