@@ -187,7 +187,11 @@ def profile_conv_kernels(tr, batch_dev):
         e0.record()
         r = orig_conv(g, a, wp, Cout, out, out_strides, *aa, **kk)
         e1.record()
-        rec["conv"].append((e0, e1, flops_conv(g, Cout), ("conv", g.N, g.Ho, g.Wo, g.C, Cout, len(g.taps), len(g.views))))
+        sig = ("conv", g.N, g.Ho, g.Wo, g.C, Cout, len(g.taps), len(g.views))
+        if os.environ.get("VQB_KERNEL_TABLE", "0") == "2":  # split rows by epilogue variant
+            sig += ("".join(c for c, k in (("b", "bias"), ("r", "res"), ("m", "mask"), ("s", "stats"))
+                            if kk.get(k) is not None) + ("R" if kk.get("relu") else ""),)
+        rec["conv"].append((e0, e1, flops_conv(g, Cout), sig))
         return r
 
     def wgrad_wrap(g, x, dy, weight_shape, Cout_pad, **kk):
@@ -216,7 +220,7 @@ def profile_conv_kernels(tr, batch_dev):
             t[0] += 1
             t[1] += e0.elapsed_time(e1)
             t[2] += f
-    if os.environ.get("VQB_KERNEL_TABLE", "0") == "1":
+    if os.environ.get("VQB_KERNEL_TABLE", "0") in ("1", "2"):
         sys.stderr.write("kind N Ho Wo C Cout taps views | launches total_ms TFLOP/s\n")
         for sig, (cnt, ms_, fl_) in sorted(table.items(), key=lambda kv: -kv[1][1]):
             sys.stderr.write(f"{sig} | {cnt} {ms_:.3f} {fl_ / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0:.1f}\n")

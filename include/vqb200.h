@@ -155,9 +155,10 @@ int vqb_gn_silu_fwd(const void* x, void* y, const float* gamma, const float* bet
 /* forward when the producing conv already accumulated chsums[N][C][2] (VQB_EPI_STATS): finalise + apply only */
 int vqb_gn_silu_fwd_pre(const void* x, void* y, const float* gamma, const float* beta, float* mr, const float* chsums,
                         int N, int HW, int C, int G, float eps, int silu, void* stream);
+/* dx_colsum (optional [C] fp32): per-channel sums of dx = bias gradient of the conv that produced x, same pass */
 int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
                     const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
-                    void* stream);
+                    float* dx_colsum, void* stream);
 
 /* nearest-neighbour x2 up-sampling (ae.py:165) and its backward (2x2 sum), bf16 NHWC */
 int vqb_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);

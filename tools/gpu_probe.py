@@ -214,15 +214,16 @@ def case_wgrad(N, H, W, Cin, Cout, k, ksplit, stride2=False, seed=0):
     return ok
 
 
-def bench_conv(N, H, W, Cin, Cout, k, iters=20):
+def bench_conv(N, H, W, Cin, Cout, k, iters=20, res=False, cudnn=True):
     torch.manual_seed(0)
     x = rnd(N, H, W, Cin).to(torch.bfloat16)
     w = rnd(Cout, Cin, k, k, scale=(Cin * k * k) ** -0.5)
     g = plans.geom_s1(N, H, W, Cin, k)
     wp = pack_torch(w, g.tapmap, False, Cin)
     out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
-    d = plans.conv_desc(g, Cout, plans.nhwc_strides(H, W, Cout), 0, False)
-    args = (d, native.ptr(x), native.ptr(wp), 0, 0, 0, native.ptr(out), 0, native.stream_ptr())
+    d = plans.conv_desc(g, Cout, plans.nhwc_strides(H, W, Cout), native.EPI_RES if res else 0, False)
+    r = rnd(N, H, W, Cout).to(torch.bfloat16) if res else None
+    args = (d, native.ptr(x), native.ptr(wp), 0, native.ptr(r), 0, native.ptr(out), 0, native.stream_ptr())
     for _ in range(3):
         native.check(L.vqb_conv_gemm(*args))
     torch.cuda.synchronize()
@@ -234,6 +235,10 @@ def bench_conv(N, H, W, Cin, Cout, k, iters=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     fl = 2.0 * N * H * W * Cout * Cin * k * k
+    if not cudnn or res:
+        print(f"BENCH conv{k}x{k} N={N} {H}x{W} {Cin}->{Cout}{' +res' if res else ''}: ours {ms:.3f} ms = "
+              f"{fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+        return
     # cudnn bf16 reference timing
     xc = x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
     wc = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -327,10 +332,12 @@ def group_elem():
         dg = torch.zeros(Cc, device=dev)
         db = torch.zeros(Cc, device=dev)
         ws2 = torch.zeros(N * Cc * 2 + N * 32 * 2, device=dev)
+        csum = torch.full((Cc,), 7.0, device=dev)
         native.check(L.vqb_gn_silu_bwd(native.ptr(xx), native.ptr(dy), native.ptr(addt), native.ptr(dx), native.ptr(gamma),
                                        native.ptr(beta), native.ptr(mr), native.ptr(dg), native.ptr(db), native.ptr(ws2),
-                                       N, H * W, Cc, 32, silu, native.stream_ptr()))
+                                       N, H * W, Cc, 32, silu, native.ptr(csum), native.stream_ptr()))
         torch.cuda.synchronize()
+        ok &= report("   bwd colsum(dx)", csum[None], dx.float().sum((0, 1, 2))[None], tol=1e-3)
         gxr, ggr, gbr = torch.autograd.grad(yr, (xr, gr, br), dy.float().permute(0, 3, 1, 2))
         ok &= report("   bwd dx(+add)", dx, gxr.permute(0, 2, 3, 1) + addt.float(), tol=1e-2)
         ok &= report("   bwd dgamma", dg[None], ggr[None], tol=1e-2)
@@ -538,6 +545,15 @@ def group_conv():
     ok &= case_conv(3, 4, 4, 64, 64, 3)
     ok &= case_conv(2, 20, 20, 64, 64, 3, bias=True)
     ok &= case_conv(1, 24, 40, 128, 64, 3)
+    # residual / mask operands arrive through TMA-prefetched tiles: ragged tiles, partial channel groups, many tiles per CTA
+    ok &= case_conv(2, 20, 20, 64, 96, 3, bias=True, res=True)
+    ok &= case_conv(3, 24, 40, 128, 32, 3, res=True, relu=True)
+    ok &= case_conv(8, 128, 128, 128, 128, 3, bias=True, res=True)
+    ok &= case_conv(8, 64, 64, 256, 256, 3, bias=True, res=True)
+    ok &= case_conv(8, 64, 64, 128, 320, 1, res=True)
+    ok &= case_conv(8, 64, 64, 128, 128, 3, mask=True)
+    ok &= case_conv(2, 20, 20, 64, 96, 3, bias=True, res=True, mask=True)
+    ok &= case_conv(5, 12, 12, 64, 64, 3, mask=True, relu=True)
     return ok
 
 
@@ -572,6 +588,17 @@ def group_wgrad():
     ok &= case_wgrad(2, 32, 32, 16, 512, 3, 2)
     ok &= case_wgrad(2, 32, 32, 128, 128, 3, 2, stride2=True)
     return ok
+
+
+def group_resbench():
+    """epilogue with a residual operand: TMA-prefetched tiles (default) vs per-thread loads (debug bit 512)"""
+    for (N, H, W, C) in [(32, 256, 256, 128), (32, 128, 128, 256), (32, 64, 64, 512), (32, 32, 32, 512)]:
+        for mode in (0, 512):
+            L.vqb_set_debug_mode(mode)
+            bench_conv(N, H, W, C, C, 3, res=True)
+        L.vqb_set_debug_mode(0)
+        bench_conv(N, H, W, C, C, 3)
+    return True
 
 
 def group_bench():

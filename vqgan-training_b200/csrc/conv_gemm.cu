@@ -28,6 +28,7 @@ struct alignas(64) ConvParams {
     CUtensorMap amap[VQB_MAX_VIEWS];
     CUtensorMap bmap;
     CUtensorMap omap;  // output tensor (TMA-store epilogue)
+    CUtensorMap xmap;  // residual (or ReLU-gate mask) tensor, same geometry as omap (TMA-prefetched epilogue operand)
     int32_t tap_view[VQB_MAX_TAPS];
     int32_t tap_dw[VQB_MAX_TAPS];
     int32_t tap_dh[VQB_MAX_TAPS];
@@ -40,7 +41,7 @@ struct alignas(64) ConvParams {
     int32_t mtiles, nbuf;
     int32_t tma_store, mt_dh, mt_dn, do_stats;  // TMA-store epilogue enabled; box offset of the second sub-tile  // 128-row accumulator sub-tiles per CTA tile (1|2); TMEM accumulator buffers (2..4)
     int32_t flags, out_f32;
-    int32_t dbg, _pad0;
+    int32_t dbg, aux_tma;  // aux_tma: 1 = residual, 2 = mask arrives through xmap
     int64_t on, oh, ow, oc;
     void* out;
     const void* res;
@@ -64,11 +65,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint8_t* sB = base + stages * a_bytes;
     uint8_t* sOut = sB + stages * b_bytes;  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
     float* sStat = reinterpret_cast<float*>(sOut + 2 * 16384);  // [4 warps][64 ch][2] (GroupNorm statistics combine)
-    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (p.tma_store ? 2 * 16384 + 2048 : 0));
+    uint8_t* sAux = sOut + 2 * 16384 + 2048;  // 2 x 16 KB residual / mask tiles (same swizzled layout as sOut)
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (p.tma_store ? 2 * 16384 + 2048 : 0) + (p.aux_tma ? 2 * 16384 : 0));
     uint64_t* empty = full + stages;
     uint64_t* tfull = empty + stages;
     uint64_t* tempty = tfull + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
+    uint64_t* afull = tempty + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 2);
 
     if (warp == 0 && lane == 0) {
         for (int v = 0; v < VQB_MAX_VIEWS; ++v) {
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         tma_prefetch_desc(&p.bmap);
         if (p.tma_store) tma_prefetch_desc(&p.omap);
+        if (p.aux_tma) tma_prefetch_desc(&p.xmap);
     }
     if (warp == 1 && lane == 0) {
         for (uint32_t i = 0; i < stages; ++i) {
@@ -88,6 +92,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 128);
         }
+        mbar_init(&afull[0], 1);
+        mbar_init(&afull[1], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -212,6 +218,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const bool vec_path = (p.oc == 1) && (p.out_f32 == 0);
         const bool no_store = (p.dbg & 128) != 0;  // experiment: drain TMEM but skip the global stores
         uint32_t ebuf = 0, epar = 0, obuf = 0;
+        // Residual / mask tiles are fetched by TMA one 64-channel group AHEAD of the group being drained (per-thread
+        // loads of this operand were latency bound: a residual epilogue ran at 0.6x the speed of a plain one). The
+        // elected thread walks the same (tile, sub-tile, channel group) sequence one step ahead.
+        const bool aux_tma = p.aux_tma != 0;
+        const bool elected = (ew == 0 && lane == 0);
+        int ptile = blockIdx.x;
+        uint32_t pmt = 0, pq = 0;
+        int pcg = 0;
+        auto aux_issue_next = [&]() {
+            if (ptile >= p.total_tiles) return;
+            const int n_tile = ptile % p.n_tiles;
+            const int m_tile = ptile / p.n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            const int th = (m_tile / p.tiles_w) % p.tiles_h;
+            const int tn = m_tile / (p.tiles_w * p.tiles_h);
+            const int col = n_tile * p.block_n + pcg * 64;
+            mbar_arrive_expect_tx(&afull[pq & 1u], 16384u);
+            tma_load_4d(&p.xmap, &afull[pq & 1u], sAux + (pq & 1u) * 16384u, col, tw << p.lbw,
+                        (th << p.lbh) + (pmt ? p.mt_dh : 0), (tn << p.lbn) + (pmt ? p.mt_dn : 0));
+            ++pq;
+            ++pcg;
+            if (pcg * 64 >= p.block_n || n_tile * p.block_n + pcg * 64 >= p.Cout) {
+                pcg = 0;
+                if (++pmt == mtiles) {
+                    pmt = 0;
+                    ptile += gridDim.x;
+                }
+            }
+        };
+        if (aux_tma && elected) aux_issue_next();  // group 0
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.n_tiles;
           const int m_tile = tile / p.n_tiles;
@@ -249,8 +285,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 for (int cg = 0; cg < ngroups; ++cg) {
                     if (col0 + cg * 64 >= p.Cout) break;  // uniform
                     uint8_t* sbuf = sOut + (obuf & 1u) * 16384u;
-                    if (ew == 0 && lane == 0) bulk_wait_read<1>();  // the store issued from this buffer has drained it
+                    if (elected) bulk_wait_read<1>();  // the store issued from this buffer has drained it
                     named_bar_sync(1, 128);
+                    // every thread is past its reads of the other aux tile (previous group): refill it for the next group
+                    if (aux_tma && elected) aux_issue_next();
+                    const uint8_t* abuf = sAux + (obuf & 1u) * 16384u;
                     // both 32-column TMEM loads of this group are issued before the single wait (latency overlap)
                     uint32_t v0[32], v1[32];
                     const int cbase = cg * 64;
@@ -258,6 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (h0) tmem_ld32(taddr + cbase, v0);
                     if (h1) tmem_ld32(taddr + cbase + 32, v1);
                     tmem_ld_wait();
+                    if (aux_tma) mbar_wait(&afull[obuf & 1u], (obuf >> 1) & 1u);
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const int c0 = cbase + c4 * 16;
@@ -275,10 +315,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
                             }
-                            if (has_res && valid) {
-                                const uint4* rp = reinterpret_cast<const uint4*>(
-                                    reinterpret_cast<const __nv_bfloat16*>(p.res) + pix + col);
-                                uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                            if (has_res && (valid || p.aux_tma == 1)) {
+                                uint4 r0, r1;
+                                if (p.aux_tma == 1) {  // out-of-range rows were zero-filled by the TMA load
+                                    const uint8_t* arow = abuf + r * 128u;
+                                    r0 = *reinterpret_cast<const uint4*>(arow + (((2 * c4) ^ (r & 7u)) << 4));
+                                    r1 = *reinterpret_cast<const uint4*>(arow + (((2 * c4 + 1) ^ (r & 7u)) << 4));
+                                } else {
+                                    const uint4* rp = reinterpret_cast<const uint4*>(
+                                        reinterpret_cast<const __nv_bfloat16*>(p.res) + pix + col);
+                                    r0 = __ldg(rp);
+                                    r1 = __ldg(rp + 1);
+                                }
                                 const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
@@ -291,10 +339,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                             }
-                            if (has_mask && valid) {
-                                const uint4* mp = reinterpret_cast<const uint4*>(
-                                    reinterpret_cast<const __nv_bfloat16*>(p.mask) + pix + col);
-                                uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                            if (has_mask && (valid || p.aux_tma == 2)) {
+                                uint4 m0, m1;
+                                if (p.aux_tma == 2) {
+                                    const uint8_t* arow = abuf + r * 128u;
+                                    m0 = *reinterpret_cast<const uint4*>(arow + (((2 * c4) ^ (r & 7u)) << 4));
+                                    m1 = *reinterpret_cast<const uint4*>(arow + (((2 * c4 + 1) ^ (r & 7u)) << 4));
+                                } else {
+                                    const uint4* mp = reinterpret_cast<const uint4*>(
+                                        reinterpret_cast<const __nv_bfloat16*>(p.mask) + pix + col);
+                                    m0 = __ldg(mp);
+                                    m1 = __ldg(mp + 1);
+                                }
                                 const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
@@ -577,7 +633,11 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     p.do_stats = (d->flags & VQB_EPI_STATS) ? 1 : 0;
     if (query_only) return stats_ok ? 1 : 0;
     const int stage_bytes = mtiles * kABytes + block_n * kBlockK * 2;
-    int stages = (227 * 1024 - 1280 - (tma_store ? 2 * 16384 + 2048 : 0)) / stage_bytes;
+    // residual / ReLU-gate operand through TMA (debug bit 512 keeps the per-thread loads)
+    const int aux_tma = (tma_store && !(p_dbg & 512)) ? ((d->flags & VQB_EPI_RES) ? 1 : ((d->flags & VQB_EPI_MASK) ? 2 : 0)) : 0;
+    p.aux_tma = aux_tma;
+    const int epi_smem = (tma_store ? 2 * 16384 + 2048 : 0) + (aux_tma ? 2 * 16384 : 0);
+    int stages = (227 * 1024 - 1280 - epi_smem) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
     int nbuf = 512 / block_n;
@@ -628,8 +688,12 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         uint32_t box[4] = {64, obw, obh, obn};
         rc = encode_tmap_bf16(&p.omap, out, 4, dims, str, box, 128);
         if (rc != VQB_OK) return rc;
+        if (aux_tma) {
+            rc = encode_tmap_bf16(&p.xmap, aux_tma == 1 ? res : mask, 4, dims, str, box, 128);
+            if (rc != VQB_OK) return rc;
+        }
     }
-    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (tma_store ? 2 * 16384 + 2048 : 0) + 256;
+    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + epi_smem + 256;
     static bool attr_set = false;
     if (!attr_set) {
         VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -371,12 +371,19 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
                                     const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
                                     const float* __restrict__ mr, const float* __restrict__ gs,
                                     const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
-                                    int G, int pix_per_chunk, int silu) {
+                                    int G, int pix_per_chunk, int silu, float* __restrict__ colsum /* [C] or null */) {
+    extern __shared__ float sm[];  // [C] (only when colsum != null)
     const int V = C >> 3, R = blockDim.x / V;
     const int cv = threadIdx.x % V, pr = threadIdx.x / V;
-    if (pr >= R) return;
+    if (colsum) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+    }
+    if (pr < R) {
     const int n = blockIdx.y, cpg = C / G;
-    float mean[8], rstd[8], ga[8], be[8], S1[8], S2[8];
+    float mean[8], rstd[8], ga[8], be[8], S1[8], S2[8], cs8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = cv * 8 + j, g = c / cpg;
@@ -418,9 +425,20 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
             float v = rstd[j] * (du * ga[j] - S1[j] - xh * S2[j]);
             if (add) v += r[j];
             f[j] = v;
+            // column sums of the bf16 values actually written (= bias gradient of the conv that produced x)
+            cs8[j] += __bfloat162float(__float2bfloat16(v));
         }
         store8(dx + off, f);
         }
+    }
+    if (colsum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], cs8[j]);
+    }
+    }
+    if (colsum) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], sm[i]);
     }
 }
 
@@ -730,9 +748,11 @@ int vqb_gn_silu_fwd_pre(const void* x, void* y, const float* gamma, const float*
 }
 
 // GroupNorm(+SiLU) backward. ws: >= N*C*2 + N*G*2 floats. dx may alias dy. add (optional) is summed into dx.
+// dx_colsum (optional, [C] fp32, overwritten): per-channel sums of dx over all N*HW pixels, i.e. the bias gradient of the
+// convolution whose output this GroupNorm normalised, produced in the same pass instead of by vqb_colsum.
 int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
                     const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
-                    void* stream) {
+                    float* dx_colsum, void* stream) {
     VQB_CHECK(x && dy && dx && gamma && beta && mr && dgamma && dbeta && ws, "vqb_gn_silu_bwd: null pointer");
     VQB_CHECK(C % 8 == 0 && C % G == 0 && C <= 2048, "vqb_gn_silu_bwd: C=%d G=%d unsupported", C, G);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -747,11 +767,13 @@ int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, co
         ppc, silu);
     const int fin = (N * G > C ? N * G : C);
     gn_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(cs, gamma, gsum, dgamma, dbeta, N, C, G, HW);
-    cv_grid(HW, C, N, gn_bwd_apply_kernel, 0, chunks, ppc);
-    gn_bwd_apply_kernel<<<dim3(chunks, N), T, 0, st>>>(
+    const size_t cs_smem = dx_colsum ? C * sizeof(float) : 0;
+    if (dx_colsum) VQB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
+    cv_grid(HW, C, N, gn_bwd_apply_kernel, cs_smem, chunks, ppc);
+    gn_bwd_apply_kernel<<<dim3(chunks, N), T, cs_smem, st>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
         static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), mr, gsum, gamma, beta, HW, C, G, ppc,
-        silu);
+        silu, dx_colsum);
     VQB_CUDA(cudaGetLastError());
     count_launch(3);
     return VQB_OK;

@@ -72,7 +72,7 @@ def load():
         "vqb_nchw_to_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "vqb_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "vqb_gn_silu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
-        "vqb_gn_silu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "vqb_gn_silu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "vqb_upsample2x_fwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vqb_upsample2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vqb_colsum": (i32, [vp, vp, i64, i32, vp]),

@@ -9,6 +9,7 @@ Every op here launches hand-written CUDA; nothing falls back to ATen for the mat
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -167,6 +168,25 @@ def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape
     check(_L().vqb_wgrad_reduce(ptr(partial), ptr(grad), ksplit, Cout, Cout_pad, Cin, KH * KW, len(g.taps),
                                 cols // len(g.taps), ptr(tm), 0, stream_ptr()), "wgrad_reduce")
     return grad
+
+
+# One-slot side channel from GroupNormSiLUFn.backward to the backward of the conv that produced the normalised tensor:
+# the GN backward apply pass already streams dx (= that conv's dy), so it also emits the per-channel sums (= the conv's
+# bias gradient). The slot holds a strong reference to dx, so a matching data_ptr can only be that very tensor; the
+# version check rejects a tensor that autograd accumulated into in place. Any mismatch falls back to vqb_colsum.
+_dx_colsum_slot = [None]
+
+
+def _take_dx_colsum(dy: torch.Tensor, C: int):
+    ent = _dx_colsum_slot[0]
+    if ent is None:
+        return None
+    t, ver, cs = ent
+    if (t.data_ptr() == dy.data_ptr() and t.shape == dy.shape and t.stride() == dy.stride() and t.dtype == dy.dtype
+            and dy._version == ver and cs.numel() == C):
+        _dx_colsum_slot[0] = None
+        return cs
+    return None
 
 
 def colsum(x2d_rows: int, x: torch.Tensor, C: int) -> torch.Tensor:
@@ -402,7 +422,9 @@ class ConvFn(torch.autograd.Function):
                 gw = run_wgrad(g, x, dy, weight.shape, Cop)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             rows = N * (g.Ho + 2) * (g.Wo + 2) if dy_framed else N * g.Ho * g.Wo  # the zero frame adds nothing
-            gb = colsum(rows, dy, Cop)[:Cout]
+            gb = None if dy_framed else _take_dx_colsum(dy, Cop)
+            if gb is None:
+                gb = colsum(rows, dy, Cop)[:Cout]
         if ctx.has_res and ctx.needs_input_grad[3]:
             gres = dy
         return gx, gw, gb, gres, None, None, None, None, None, None
@@ -492,7 +514,9 @@ class UpConvFn(torch.autograd.Function):
             check(_L().vqb_wgrad_reduce_fold(ptr(partial), ptr(gw), ksplit, Cout, Cop, Cin, 9, 16, C64, ptr(tm),
                                              stream_ptr()), "wgrad_reduce_fold")
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = colsum(N * 4 * h * w, dy, Cop)[:Cout]
+            gb = _take_dx_colsum(dy, Cop)
+            if gb is None:
+                gb = colsum(N * 4 * h * w, dy, Cop)[:Cout]
         return gx, gw, gb, None, None
 
 
@@ -501,6 +525,9 @@ def upsample_conv(x, weight, bias, cache, want_stats=False):
         out, st = UpConvFn.apply(x, weight, bias, cache, True)
         return out, (st if st.numel() > 0 else None)
     return UpConvFn.apply(x, weight, bias, cache, False)
+
+
+_GN_COLSUM = os.environ.get("VQB_GN_COLSUM", "1") == "1"
 
 
 class GroupNormSiLUFn(torch.autograd.Function):
@@ -546,8 +573,11 @@ class GroupNormSiLUFn(torch.autograd.Function):
         db = torch.empty(C, device=x.device, dtype=torch.float32)
         ws = torch.empty(N * C * 2 + N * ctx.groups * 2, device=x.device, dtype=torch.float32)
         ga, be = gamma.detach().float(), beta.detach().float()
+        cs = torch.empty(C, device=x.device, dtype=torch.float32) if _GN_COLSUM else None
         check(_L().vqb_gn_silu_bwd(ptr(x), ptr(gy), ptr(add), ptr(dx), ptr(ga), ptr(be), ptr(mr), ptr(dg), ptr(db),
-                                   ptr(ws), N, H * W, C, ctx.groups, 1 if ctx.silu else 0, stream_ptr()), "gn_silu_bwd")
+                                   ptr(ws), N, H * W, C, ctx.groups, 1 if ctx.silu else 0, ptr(cs), stream_ptr()),
+              "gn_silu_bwd")
+        _dx_colsum_slot[0] = (dx, dx._version, cs) if cs is not None else None
         return dx, dg, db, None, None, None, None, None
 
 
