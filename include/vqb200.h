@@ -160,6 +160,11 @@ int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, co
                     const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
                     float* dx_colsum, void* stream);
 
+/* bring-up experiment only (csrc/dbg_shift.cu): one M=128,N=64,K=64 MMA whose A descriptor starts shift_rows rows into a
+ * TMA-written 128B-swizzled tile with 8-row groups sbo_bytes apart */
+int vqb_dbg_shift_mma(const void* X, int R, const void* B, float* out, int shift_rows, int sbo_bytes, int base_offset,
+                      void* stream);
+
 /* nearest-neighbour x2 up-sampling (ae.py:165) and its backward (2x2 sum), bf16 NHWC */
 int vqb_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
 int vqb_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream);

@@ -590,6 +590,46 @@ def group_wgrad():
     return ok
 
 
+def group_shift():
+    """descriptor-shift experiment (csrc/dbg_shift.cu): which (row shift, SBO, base_offset) combinations give the expected
+    rows? Decides the halo-tile conv design."""
+    torch.manual_seed(0)
+    R = 512
+    X = rnd(R, 64).to(torch.bfloat16)
+    B = rnd(64, 64).to(torch.bfloat16)
+    out = torch.zeros(128, 64, device=dev)
+    m = torch.arange(128, device=dev)
+    for sbo in (1024, 1280, 2048, 2304, 3072):
+        for shift in (0, 1, 2, 3, 8, 9, 17, 34):
+            res = []
+            for bo_name, bo in (("0", 0), ("rows&7", shift & 7)):
+                out.zero_()
+                native.check(L.vqb_dbg_shift_mma(native.ptr(X), R, native.ptr(B), native.ptr(out), shift, sbo, bo,
+                                                 native.stream_ptr()))
+                torch.cuda.synchronize()
+                rows = shift + (m // 8) * (sbo // 128) + (m % 8)
+                ref = X[rows].float() @ B.float().t()
+                err = ((out - ref).norm() / ref.norm()).item()
+                res.append(f"bo={bo_name}: {'OK ' if err < 1e-3 else 'BAD'} ({err:.1e})")
+            print(f"SHIFT sbo={sbo} shift={shift}: " + " | ".join(res), flush=True)
+    return True
+
+
+def group_halobench():
+    """3x3 convs: halo-tile mode (default) vs one TMA box per tap (debug bit 1024)"""
+    for (N, H, W, Ci, Co) in [(32, 256, 256, 128, 128), (32, 128, 128, 256, 256), (32, 64, 64, 512, 512),
+                              (32, 32, 32, 512, 512), (32, 16, 16, 512, 512), (32, 128, 128, 128, 256),
+                              (32, 256, 256, 64, 64)]:
+        for mode in (0, 1024):
+            L.vqb_set_debug_mode(mode)
+            print(f"[dbg={mode}]", end=" ")
+            bench_conv(N, H, W, Ci, Co, 3, cudnn=(mode == 1024))
+        L.vqb_set_debug_mode(0)
+        print("[dbg=0]", end=" ")
+        bench_conv(N, H, W, Ci, Co, 3, res=True)
+    return True
+
+
 def group_resbench():
     """epilogue with a residual operand: TMA-prefetched tiles (default) vs per-thread loads (debug bit 512)"""
     for (N, H, W, C) in [(32, 256, 256, 128), (32, 128, 128, 256), (32, 64, 64, 512), (32, 32, 32, 512)]:

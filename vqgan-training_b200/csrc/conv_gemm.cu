@@ -42,6 +42,10 @@ struct alignas(64) ConvParams {
     int32_t tma_store, mt_dh, mt_dn, do_stats;  // TMA-store epilogue enabled; box offset of the second sub-tile  // 128-row accumulator sub-tiles per CTA tile (1|2); TMEM accumulator buffers (2..4)
     int32_t flags, out_f32;
     int32_t dbg, aux_tma;  // aux_tma: 1 = residual, 2 = mask arrives through xmap
+    // halo mode: ONE activation box with a halo serves every tap of a 64-channel chunk (tap shift = descriptor offset)
+    int32_t halo, h_bytes, h_stages, h_sbo;  // enabled; bytes per halo stage (1024-aligned); stages; 8-row group stride
+    int32_t h_w0, h_h0, mt_dw, h_tx;         // most negative tap offsets (box origin); w offset of the second sub-tile; box bytes
+    uint32_t tap_off16[VQB_MAX_TAPS];        // descriptor start offset of tap t inside the halo tile, in 16-byte units
     int64_t on, oh, ow, oc;
     void* out;
     const void* res;
@@ -61,8 +65,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t a_bytes = static_cast<uint32_t>(p.mtiles) * kABytes;
     const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
     const uint32_t mtiles = p.mtiles, nbuf = p.nbuf;
-    uint8_t* sA = base;
-    uint8_t* sB = base + stages * a_bytes;
+    uint8_t* sA = base;  // halo mode: h_stages halo tiles; else `stages` 128-row tap tiles
+    uint8_t* sB = base + (p.halo ? static_cast<uint32_t>(p.h_stages * p.h_bytes) : stages * a_bytes);
     uint8_t* sOut = sB + stages * b_bytes;  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
     float* sStat = reinterpret_cast<float*>(sOut + 2 * 16384);  // [4 warps][64 ch][2] (GroupNorm statistics combine)
     uint8_t* sAux = sOut + 2 * 16384 + 2048;  // 2 x 16 KB residual / mask tiles (same swizzled layout as sOut)
@@ -71,7 +75,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint64_t* tfull = empty + stages;
     uint64_t* tempty = tfull + 4;
     uint64_t* afull = tempty + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 2);
+    uint64_t* hfull = afull + 2;   // halo ring (<= 4 stages)
+    uint64_t* hempty = hfull + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty + 4);
 
     if (warp == 0 && lane == 0) {
         for (int v = 0; v < VQB_MAX_VIEWS; ++v) {
@@ -94,6 +100,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         mbar_init(&afull[0], 1);
         mbar_init(&afull[1], 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&hfull[i], 1);
+            mbar_init(&hempty[i], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -107,7 +117,57 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     const int num_kb = p.ntaps * p.kchunks;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && lane == 0 && p.halo) {
+        // ===================== TMA producer, halo mode: per 64-channel chunk ONE activation box (tile + halo) and one
+        // weight tile per tap. The activation bytes per FLOP drop by ~ntaps/1.3; the weight tiles stream through
+        // their own ring.
+        uint32_t stage = 0, phase = 0, hs = 0, hph = 0;
+        uint8_t* b_dst = sB;
+        uint8_t* h_dst = sA;
+        const uint32_t h_tx = static_cast<uint32_t>(p.h_tx);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            const int m_tile = tile / p.n_tiles;
+            const int tw = m_tile % p.tiles_w;
+            const int th = (m_tile / p.tiles_w) % p.tiles_h;
+            const int tn = m_tile / (p.tiles_w * p.tiles_h);
+            const int w0 = (tw << p.lbw) + p.h_w0, h0 = (th << p.lbh) + p.h_h0;
+            const int ncol0 = n_tile * p.block_n;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&hempty[hs], hph ^ 1);
+                if ((p.dbg & 3) == 1) {
+                    mbar_arrive(&hfull[hs]);
+                } else {
+                    mbar_arrive_expect_tx(&hfull[hs], h_tx);
+                    tma_load_4d(&p.amap[0], &hfull[hs], h_dst, kc * kBlockK, w0, h0, tn);
+                }
+                if (++hs == static_cast<uint32_t>(p.h_stages)) {
+                    hs = 0;
+                    hph ^= 1;
+                    h_dst = sA;
+                } else {
+                    h_dst += p.h_bytes;
+                }
+                int kcol = kc * kBlockK;
+                for (int t = 0; t < p.ntaps; ++t, kcol += p.C) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if ((p.dbg & 3) == 1) {
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], b_bytes);
+                        tma_load_2d(&p.bmap, &full[stage], b_dst, kcol, ncol0);
+                    }
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1;
+                        b_dst = sB;
+                    } else {
+                        b_dst += b_bytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 0 && lane == 0) {
         // ===================== TMA producer (one thread; keep the per-K-block instruction count small) =========
         uint32_t stage = 0, phase = 0, tile_iter = 0;
         uint8_t* a_dst = sA;
@@ -161,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;  // descriptor address field is (addr >> 4)
         const bool two = (mtiles == 2);
         const bool do_mma = (p.dbg & 3) != 2;
-        uint32_t stage = 0, phase = 0, a_off = 0, b_off = 0;
+        uint32_t stage = 0, phase = 0, a_off = 0, b_off = 0, hstage = 0, hphase = 0;
         uint32_t buf = 0, bpar = 0;  // next TMEM accumulator buffer and the parity of its use count
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const uint32_t b0 = buf;
@@ -182,6 +242,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             tc_fence_after();
             const uint32_t d0 = tmem_base + b0 * p.block_n, d1 = tmem_base + b1 * p.block_n;
             uint32_t acc = 0;
+            if (p.halo) {
+                // halo mode: the A descriptor of tap t is the halo tile's descriptor plus a row offset (the 128B swizzle is
+                // a function of absolute smem address bits, so row-shifted starts and an 8-row group stride of one
+                // halo-tile line read exactly the rows the TMA unit wrote: tools/gpu_probe.py shift)
+                const uint64_t dh_base = make_smem_desc(smem_u32(sA), 0, static_cast<uint32_t>(p.h_sbo), 2);
+                const uint32_t h_step = static_cast<uint32_t>(p.h_bytes) >> 4;
+                const uint32_t mt_off = static_cast<uint32_t>(p.mt_dw) * 8u;  // mt_dw rows of 128 B, in 16-byte units
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&hfull[hstage], hphase);
+                    const uint64_t dah = dh_base + hstage * h_step;
+                    for (int t = 0; t < p.ntaps; ++t) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t da = dah + p.tap_off16[t], db = db_base + b_off;
+                        if (do_mma) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d0, da + 2 * k, db + 2 * k, idesc, acc | k);
+                            if (two) {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16(d1, da + mt_off + 2 * k, db + 2 * k, idesc, acc | k);
+                            }
+                        }
+                        umma_commit(&empty[stage]);
+                        acc = 1;
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                            b_off = 0;
+                        } else {
+                            b_off += b_step;
+                        }
+                    }
+                    umma_commit(&hempty[hstage]);  // every tap of this chunk has been issued: the halo tile may be refilled
+                    if (++hstage == static_cast<uint32_t>(p.h_stages)) {
+                        hstage = 0;
+                        hphase ^= 1;
+                    }
+                }
+            } else
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
@@ -235,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int tn = m_tile / (p.tiles_w * p.tiles_h);
             const int col = n_tile * p.block_n + pcg * 64;
             mbar_arrive_expect_tx(&afull[pq & 1u], 16384u);
-            tma_load_4d(&p.xmap, &afull[pq & 1u], sAux + (pq & 1u) * 16384u, col, tw << p.lbw,
+            tma_load_4d(&p.xmap, &afull[pq & 1u], sAux + (pq & 1u) * 16384u, col, (tw << p.lbw) + (pmt ? p.mt_dw : 0),
                         (th << p.lbh) + (pmt ? p.mt_dh : 0), (tn << p.lbn) + (pmt ? p.mt_dn : 0));
             ++pq;
             ++pcg;
@@ -262,9 +362,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 epar ^= 1;
             }
             const uint32_t row = mt * 128 + ew * 32 + lane;  // row of the (128*mtiles)-pixel box
-            const int wi = row & ((1 << p.lbw) - 1);
-            const int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
-            const int ni = row >> (p.lbw + p.lbh);
+            int wi = row & ((1 << p.lbw) - 1);
+            int hi = (row >> p.lbw) & ((1 << p.lbh) - 1);
+            int ni = row >> (p.lbw + p.lbh);
+            if (p.halo) {  // sub-tile = 8 columns x 16 rows, second sub-tile to the right
+                wi = static_cast<int>((row & 7u) + mt * 8u);
+                hi = static_cast<int>((row >> 3) & 15u);
+                ni = 0;
+            }
             const int w = (tw << p.lbw) + wi, h = (th << p.lbh) + hi, n = (tn << p.lbn) + ni;
             const bool valid = (w < p.W) && (h < p.H) && (n < p.N) && !no_store;
             const int64_t pix = static_cast<int64_t>(n) * p.on + static_cast<int64_t>(h) * p.oh +
@@ -277,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 // -------- staged epilogue: registers -> 128B-swizzled smem tile -> one TMA store per 64 channels.
                 // (direct per-thread stores write 32 B per lane at a 2*Cout-byte pitch: measured to cost up to half of the
                 // kernel time on short-K layers)
-                const int ow0 = tw << p.lbw;
+                const int ow0 = (tw << p.lbw) + (mt ? p.mt_dw : 0);
                 const int oh0 = (th << p.lbh) + (mt ? p.mt_dh : 0);
                 const int on0 = (tn << p.lbn) + (mt ? p.mt_dn : 0);
                 const uint32_t r = ew * 32 + lane;
@@ -563,10 +668,32 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         VQB_CHECK(d->taps[t].view >= 0 && d->taps[t].view < d->nviews, "vqb_conv_gemm: tap %d view out of range", t);
     if (!query_only && !device_is_sm100()) return set_error(VQB_ENODEVICE, "vqb_conv_gemm: current device is not sm_100");
 
-    ConvParams p;  // ~2.5 KB, filled per call, passed by value (__grid_constant__) to the kernel
+    ConvParams p;  // ~2.7 KB, filled per call, passed by value (__grid_constant__) to the kernel
     const int p_dbg = debug_mode();
+    // Halo mode: one dense view, taps = shifts within a <= 3x3 window, 64-channel chunks, staged bf16 NHWC output.
+    // Tile = 16 x 16 output pixels of one image (two 8 x 16 sub-tiles side by side) x 128 output channels.
+    // (Cout < 128: 64-column MMAs are issue/smem bound either way and the per-tap path measured ~10 % faster)
+    bool halo = !(p_dbg & 1024) && d->nviews == 1 && d->ntaps >= 2 && d->C % 64 == 0 && d->W > 8 && d->H > 8 &&
+                d->oc == 1 && !d->out_f32 && d->Cout % 16 == 0 && d->Cout >= 128 && !(p_dbg & 256);
+    int dwmin = 0, dwmax = 0, dhmin = 0, dhmax = 0;
+    if (halo) {
+        dwmin = dwmax = d->taps[0].dw;
+        dhmin = dhmax = d->taps[0].dh;
+        for (int t = 0; t < d->ntaps; ++t) {
+            dwmin = d->taps[t].dw < dwmin ? d->taps[t].dw : dwmin;
+            dwmax = d->taps[t].dw > dwmax ? d->taps[t].dw : dwmax;
+            dhmin = d->taps[t].dh < dhmin ? d->taps[t].dh : dhmin;
+            dhmax = d->taps[t].dh > dhmax ? d->taps[t].dh : dhmax;
+        }
+        if (dwmax - dwmin > 2 || dhmax - dhmin > 2) halo = false;
+    }
     int block_n;
-    if (d->Cout >= 256)
+    // N = 256 keeps the MMA's shared-memory operand reads under 128 B/clk (an M128 x N128 x K16 MMA reads 8 KB in its 64
+    // cycles: exactly the limit); with 256 columns one 8 x 16 sub-tile per CTA tile leaves room for TMEM double buffering.
+    const int halo_mtiles = (d->Cout >= 256 && !(p_dbg & 2048)) ? 1 : 2;
+    if (halo)
+        block_n = d->Cout >= 256 ? (halo_mtiles == 1 ? 256 : 128) : (d->Cout >= 128 ? 128 : ((d->Cout + 31) / 32) * 32);
+    else if (d->Cout >= 256)
         block_n = 256;
     else
         block_n = ((d->Cout + 15) / 16) * 16;
@@ -600,6 +727,12 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         bh = bh2;
         bn = bn2;
     }
+    if (halo) {
+        mtiles = halo_mtiles;
+        bw = 8 * mtiles;
+        bh = 16;
+        bn = 1;
+    }
     p.mtiles = mtiles;
     p.lbw = ilog2(bw);
     p.lbh = ilog2(bh);
@@ -614,7 +747,12 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     p.mt_dh = 0;
     p.mt_dn = 0;
     uint32_t obw = bw, obh = bh, obn = bn;  // 128-pixel store box = one accumulator sub-tile
-    if (mtiles == 2) {
+    p.mt_dw = 0;
+    p.halo = halo ? 1 : 0;
+    if (halo) {
+        obw = 8;
+        p.mt_dw = 8;
+    } else if (mtiles == 2) {
         if (bn >= 2) {
             obn = bn / 2;
             p.mt_dn = static_cast<int32_t>(obn);
@@ -637,8 +775,28 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     const int aux_tma = (tma_store && !(p_dbg & 512)) ? ((d->flags & VQB_EPI_RES) ? 1 : ((d->flags & VQB_EPI_MASK) ? 2 : 0)) : 0;
     p.aux_tma = aux_tma;
     const int epi_smem = (tma_store ? 2 * 16384 + 2048 : 0) + (aux_tma ? 2 * 16384 : 0);
-    int stages = (227 * 1024 - 1280 - epi_smem) / stage_bytes;
-    if (stages > kMaxStages) stages = kMaxStages;
+    int stages = (227 * 1024 - 1536 - epi_smem) / stage_bytes;
+    size_t ring_bytes = 0;
+    p.h_bytes = p.h_stages = p.h_sbo = p.h_w0 = p.h_h0 = p.h_tx = 0;
+    if (halo) {
+        const int P = 8 * mtiles + (dwmax - dwmin), Q = 16 + (dhmax - dhmin);
+        p.h_sbo = P * 128;
+        p.h_tx = P * Q * 128;
+        p.h_bytes = (p.h_tx + 1023) / 1024 * 1024;
+        p.h_stages = 2;
+        p.h_w0 = dwmin;
+        p.h_h0 = dhmin;
+        const int b_bytes = block_n * kBlockK * 2;
+        stages = (227 * 1024 - 1536 - epi_smem - p.h_stages * p.h_bytes) / b_bytes;
+        if (stages > kMaxStages) stages = kMaxStages;
+        VQB_CHECK(stages >= 2, "vqb_conv_gemm: halo mode does not fit in shared memory");
+        ring_bytes = static_cast<size_t>(p.h_stages) * p.h_bytes + static_cast<size_t>(stages) * b_bytes;
+        for (int t = 0; t < d->ntaps; ++t)
+            p.tap_off16[t] = static_cast<uint32_t>(((d->taps[t].dh - dhmin) * P + (d->taps[t].dw - dwmin)) * 8);
+    } else {
+        if (stages > kMaxStages) stages = kMaxStages;
+        ring_bytes = static_cast<size_t>(stages) * stage_bytes;
+    }
     p.stages = stages;
     int nbuf = 512 / block_n;
     if (nbuf > 4) nbuf = 4;
@@ -672,6 +830,17 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     }
     int rc = fill_views(d->views, d->nviews, a, d->C, p.lbw, p.lbh, p.lbn, p.amap);
     if (rc != VQB_OK) return rc;
+    if (halo) {  // the activation box is the 16 x 16 tile plus its halo
+        const VqbView& vw = d->views[0];
+        uint64_t dims[4] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(vw.Wv), static_cast<uint64_t>(vw.Hv),
+                            static_cast<uint64_t>(vw.Nv)};
+        uint64_t str[3] = {static_cast<uint64_t>(vw.sw) * 2, static_cast<uint64_t>(vw.sh) * 2,
+                           static_cast<uint64_t>(vw.sn) * 2};
+        uint32_t box[4] = {kBlockK, static_cast<uint32_t>(8 * mtiles + dwmax - dwmin),
+                           static_cast<uint32_t>(16 + dhmax - dhmin), 1};
+        rc = encode_tmap_bf16(&p.amap[0], static_cast<const uint8_t*>(a) + vw.offset * 2, 4, dims, str, box, 128);
+        if (rc != VQB_OK) return rc;
+    }
     {
         const uint64_t ktot = static_cast<uint64_t>(d->ntaps) * d->C;
         uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->Cout)};
@@ -693,7 +862,7 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
             if (rc != VQB_OK) return rc;
         }
     }
-    const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + epi_smem + 256;
+    const size_t smem = 1024 + ring_bytes + epi_smem + 512;
     static bool attr_set = false;
     if (!attr_set) {
         VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -73,6 +73,7 @@ def load():
         "vqb_nhwc_to_nchw": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "vqb_gn_silu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
         "vqb_gn_silu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+        "vqb_dbg_shift_mma": (i32, [vp, i32, vp, vp, i32, i32, i32, vp]),
         "vqb_upsample2x_fwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vqb_upsample2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vqb_colsum": (i32, [vp, vp, i64, i32, vp]),
