@@ -554,6 +554,15 @@ def group_conv():
     ok &= case_conv(8, 64, 64, 128, 128, 3, mask=True)
     ok &= case_conv(2, 20, 20, 64, 96, 3, bias=True, res=True, mask=True)
     ok &= case_conv(5, 12, 12, 64, 64, 3, mask=True, relu=True)
+    # Cout = 128, H >= 32 with the experimental swap mode (debug bit 4096: weights as the M operand, transposed epilogue)
+    # and without it: ragged tiles, every epilogue operand
+    for mode in (4096, 0):
+        L.vqb_set_debug_mode(mode)
+        ok &= case_conv(3, 40, 20, 128, 128, 3, bias=True, res=True, relu=True)
+        ok &= case_conv(2, 48, 24, 64, 128, 3, bias=True, mask=True)
+        ok &= case_conv(9, 64, 64, 256, 128, 3, bias=True)
+        ok &= case_conv(4, 128, 128, 128, 128, 3, res=True)
+    L.vqb_set_debug_mode(0)
     return ok
 
 

@@ -46,6 +46,10 @@ struct alignas(64) ConvParams {
     int32_t halo, h_bytes, h_stages, h_sbo;  // enabled; bytes per halo stage (1024-aligned); stages; 8-row group stride
     int32_t h_w0, h_h0, mt_dw, h_tx;         // most negative tap offsets (box origin); w offset of the second sub-tile; box bytes
     uint32_t tap_off16[VQB_MAX_TAPS];        // descriptor start offset of tap t inside the halo tile, in 16-byte units
+    // swap mode (halo mode, Cout <= 128): the weights are the M = 128 operand and 256 pixels (8 x 32) the N operand, so
+    // each MMA is M128 x N256 (96 B/clk of shared-memory operand reads instead of the 128 B/clk of an N = 128 MMA);
+    // the accumulator is [channel lane][pixel column] and the epilogue transposes through the staging tiles.
+    int32_t swap, epi_bytes;
     int64_t on, oh, ow, oc;
     void* out;
     const void* res;
@@ -63,14 +67,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t stages = p.stages;
     const uint32_t a_bytes = static_cast<uint32_t>(p.mtiles) * kABytes;
-    const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kBlockK * 2;
+    const uint32_t b_bytes = static_cast<uint32_t>(p.swap ? 128 : p.block_n) * kBlockK * 2;
     const uint32_t mtiles = p.mtiles, nbuf = p.nbuf;
     uint8_t* sA = base;  // halo mode: h_stages halo tiles; else `stages` 128-row tap tiles
     uint8_t* sB = base + (p.halo ? static_cast<uint32_t>(p.h_stages * p.h_bytes) : stages * a_bytes);
     uint8_t* sOut = sB + stages * b_bytes;  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
     float* sStat = reinterpret_cast<float*>(sOut + 2 * 16384);  // [4 warps][64 ch][2] (GroupNorm statistics combine)
     uint8_t* sAux = sOut + 2 * 16384 + 2048;  // 2 x 16 KB residual / mask tiles (same swizzled layout as sOut)
-    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (p.tma_store ? 2 * 16384 + 2048 : 0) + (p.aux_tma ? 2 * 16384 : 0));
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + p.epi_bytes);
     uint64_t* empty = full + stages;
     uint64_t* tfull = empty + stages;
     uint64_t* tempty = tfull + 4;
@@ -256,7 +260,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint64_t da = dah + p.tap_off16[t], db = db_base + b_off;
-                        if (do_mma) {
+                        if (do_mma && p.swap) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d0, db + 2 * k, da + 2 * k, idesc, acc | k);
+                        } else if (do_mma) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d0, da + 2 * k, db + 2 * k, idesc, acc | k);
                             if (two) {
@@ -317,6 +324,100 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const bool do_relu = p.flags & VQB_EPI_RELU, has_mask = p.flags & VQB_EPI_MASK;
         const bool vec_path = (p.oc == 1) && (p.out_f32 == 0);
         const bool no_store = (p.dbg & 128) != 0;  // experiment: drain TMEM but skip the global stores
+        if (p.swap) {
+            // -------- transposed epilogue: accumulator lane = output channel, column = pixel of the 8 x 32 tile.
+            // Four 16 KB staging tiles = 2 sets x (channels 0-63, 64-127) of one 8 x 16 sub-tile; a set is filled by TMA
+            // with the residual / mask tile one step ahead (when there is one), updated IN PLACE, then TMA-stored.
+            const uint32_t co = ew * 32 + lane;
+            const uint32_t half = ew >> 1;
+            const uint32_t cchunk = (co & 63u) >> 3, cin = (co & 7u) * 2u;
+            const bool co_ok = static_cast<int>(co) < p.Cout;
+            const float bias_v = (has_bias && co_ok) ? __ldg(p.bias + co) : 0.f;
+            const bool aux_tma = p.aux_tma != 0;
+            const bool elected = (ew == 0 && lane == 0);
+            uint32_t ebuf = 0, epar = 0, step = 0;
+            int ptile = blockIdx.x;
+            uint32_t ps = 0, pstep = 0;
+            auto aux_issue_next = [&]() {
+                if (ptile >= p.total_tiles) return;
+                const int tw = ptile % p.tiles_w;
+                const int th = (ptile / p.tiles_w) % p.tiles_h;
+                const int tn = ptile / (p.tiles_w * p.tiles_h);
+                uint8_t* dst = sOut + (pstep & 1u) * 32768u;
+                mbar_arrive_expect_tx(&afull[pstep & 1u], 32768u);
+                tma_load_4d(&p.xmap, &afull[pstep & 1u], dst, 0, tw << 3, (th << 5) + static_cast<int>(ps) * 16, tn);
+                tma_load_4d(&p.xmap, &afull[pstep & 1u], dst + 16384, 64, tw << 3, (th << 5) + static_cast<int>(ps) * 16, tn);
+                ++pstep;
+                ps ^= 1u;
+                if (ps == 0) ptile += gridDim.x;
+            };
+            if (aux_tma && elected) aux_issue_next();  // step 0
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int tw = tile % p.tiles_w;
+                const int th = (tile / p.tiles_w) % p.tiles_h;
+                const int tn = tile / (p.tiles_w * p.tiles_h);
+                const uint32_t as = ebuf, aph = epar;
+                if (++ebuf == nbuf) {
+                    ebuf = 0;
+                    epar ^= 1;
+                }
+                mbar_wait(&tfull[as], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + as * p.block_n;
+                float ssum = 0.f, ssq = 0.f;
+                for (uint32_t sub = 0; sub < 2; ++sub, ++step) {
+                    uint8_t* set = sOut + (step & 1u) * 32768u + half * 16384u;
+                    if (elected) {
+                        if (aux_tma) {
+                            bulk_wait_read<0>();  // the other set's store has drained: refill it for the next step
+                            aux_issue_next();
+                        } else {
+                            bulk_wait_read<1>();  // this set's previous store (two steps ago) has drained
+                        }
+                    }
+                    named_bar_sync(1, 128);
+                    if (aux_tma) mbar_wait(&afull[step & 1u], (step >> 1) & 1u);
+#pragma unroll 1
+                    for (uint32_t chunk = 0; chunk < 4; ++chunk) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + sub * 128u + chunk * 32u, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (uint32_t i = 0; i < 32; ++i) {
+                            __nv_bfloat16* cell = reinterpret_cast<__nv_bfloat16*>(
+                                set + (chunk * 32u + i) * 128u + (((cchunk ^ (i & 7u)) << 4) | cin));
+                            float f = __uint_as_float(v[i]) + bias_v;
+                            if (p.aux_tma == 1) f += __bfloat162float(*cell);
+                            if (do_relu) f = fmaxf(f, 0.f);
+                            if (p.aux_tma == 2 && !(__bfloat162float(*cell) > 0.f)) f = 0.f;
+                            const __nv_bfloat16 b = __float2bfloat16(f);
+                            if (p.do_stats) {
+                                const float fb = __bfloat162float(b);
+                                ssum += fb;
+                                ssq = fmaf(fb, fb, ssq);
+                            }
+                            *cell = b;
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (elected && !no_store) {
+                        uint8_t* s0 = sOut + (step & 1u) * 32768u;
+                        const int oh0 = (th << 5) + static_cast<int>(sub) * 16;
+                        tma_store_4d(&p.omap, s0, 0, tw << 3, oh0, tn);
+                        if (p.Cout > 64) tma_store_4d(&p.omap, s0 + 16384, 64, tw << 3, oh0, tn);
+                        bulk_commit();
+                    }
+                }
+                if (p.do_stats && co_ok) {
+                    atomicAdd(p.stats + (static_cast<int64_t>(tn) * p.Cout + co) * 2, ssum);
+                    atomicAdd(p.stats + (static_cast<int64_t>(tn) * p.Cout + co) * 2 + 1, ssq);
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty[as]);
+            }
+            if (elected) bulk_wait_all();
+        } else {
         uint32_t ebuf = 0, epar = 0, obuf = 0;
         // Residual / mask tiles are fetched by TMA one 64-channel group AHEAD of the group being drained (per-thread
         // loads of this operand were latency bound: a residual epilogue ran at 0.6x the speed of a plain one). The
@@ -598,6 +699,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
         if (p.tma_store && ew == 0 && lane == 0) bulk_wait_all();  // smem must outlive the last bulk stores
+        }
     }
 
     tc_fence_before();
@@ -688,17 +790,26 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         if (dwmax - dwmin > 2 || dhmax - dhmin > 2) halo = false;
     }
     int block_n;
+    const bool f_res = d->flags & VQB_EPI_RES, f_mask = d->flags & VQB_EPI_MASK;
+    const bool swap = halo && d->Cout > 64 && d->Cout <= 128 && d->H >= 32 && !(f_res && f_mask) &&
+                      !((f_res || f_mask) && (p_dbg & 512)) && (p_dbg & 4096);
+    // (swap mode is OFF by default: measured 906 vs 1164 TFLOP/s on 128->128 @ 256^2 — the transposed epilogue's 16-bit
+    //  shared-memory stores/loads compete with the MMA operand reads for the shared-memory port and stop overlapping;
+    //  kept behind debug bit 4096 with its tests for the stmatrix-based epilogue that would fix it)
     // N = 256 keeps the MMA's shared-memory operand reads under 128 B/clk (an M128 x N128 x K16 MMA reads 8 KB in its 64
     // cycles: exactly the limit); with 256 columns one 8 x 16 sub-tile per CTA tile leaves room for TMEM double buffering.
     const int halo_mtiles = (d->Cout >= 256 && !(p_dbg & 2048)) ? 1 : 2;
-    if (halo)
+    if (swap)
+        block_n = 256;  // accumulator columns = pixels
+    else if (halo)
         block_n = d->Cout >= 256 ? (halo_mtiles == 1 ? 256 : 128) : (d->Cout >= 128 ? 128 : ((d->Cout + 31) / 32) * 32);
     else if (d->Cout >= 256)
         block_n = 256;
     else
         block_n = ((d->Cout + 15) / 16) * 16;
     p.block_n = block_n;
-    p.n_tiles = (d->Cout + block_n - 1) / block_n;
+    p.n_tiles = swap ? 1 : (d->Cout + block_n - 1) / block_n;
+    p.swap = swap ? 1 : 0;
     // Pixel box per CTA tile: 128*mtiles output pixels. mtiles = 2 shares every weight tile between two 128-row
     // accumulators (25-33 % less L2->SM traffic per FLOP, the measured limiter); it is used when it does not cost
     // more in wave quantisation than it gains.
@@ -728,9 +839,9 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         bn = bn2;
     }
     if (halo) {
-        mtiles = halo_mtiles;
+        mtiles = swap ? 1 : halo_mtiles;
         bw = 8 * mtiles;
-        bh = 16;
+        bh = swap ? 32 : 16;
         bn = 1;
     }
     p.mtiles = mtiles;
@@ -751,6 +862,7 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     p.halo = halo ? 1 : 0;
     if (halo) {
         obw = 8;
+        obh = 16;
         p.mt_dw = 8;
     } else if (mtiles == 2) {
         if (bn >= 2) {
@@ -774,19 +886,20 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     // residual / ReLU-gate operand through TMA (debug bit 512 keeps the per-thread loads)
     const int aux_tma = (tma_store && !(p_dbg & 512)) ? ((d->flags & VQB_EPI_RES) ? 1 : ((d->flags & VQB_EPI_MASK) ? 2 : 0)) : 0;
     p.aux_tma = aux_tma;
-    const int epi_smem = (tma_store ? 2 * 16384 + 2048 : 0) + (aux_tma ? 2 * 16384 : 0);
+    const int epi_smem = swap ? 4 * 16384 + 2048 : (tma_store ? 2 * 16384 + 2048 : 0) + (aux_tma ? 2 * 16384 : 0);
+    p.epi_bytes = epi_smem;
     int stages = (227 * 1024 - 1536 - epi_smem) / stage_bytes;
     size_t ring_bytes = 0;
     p.h_bytes = p.h_stages = p.h_sbo = p.h_w0 = p.h_h0 = p.h_tx = 0;
     if (halo) {
-        const int P = 8 * mtiles + (dwmax - dwmin), Q = 16 + (dhmax - dhmin);
+        const int P = 8 * mtiles + (dwmax - dwmin), Q = (swap ? 32 : 16) + (dhmax - dhmin);
         p.h_sbo = P * 128;
         p.h_tx = P * Q * 128;
         p.h_bytes = (p.h_tx + 1023) / 1024 * 1024;
         p.h_stages = 2;
         p.h_w0 = dwmin;
         p.h_h0 = dhmin;
-        const int b_bytes = block_n * kBlockK * 2;
+        const int b_bytes = (swap ? 128 : block_n) * kBlockK * 2;
         stages = (227 * 1024 - 1536 - epi_smem - p.h_stages * p.h_bytes) / b_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
         VQB_CHECK(stages >= 2, "vqb_conv_gemm: halo mode does not fit in shared memory");
@@ -837,7 +950,7 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         uint64_t str[3] = {static_cast<uint64_t>(vw.sw) * 2, static_cast<uint64_t>(vw.sh) * 2,
                            static_cast<uint64_t>(vw.sn) * 2};
         uint32_t box[4] = {kBlockK, static_cast<uint32_t>(8 * mtiles + dwmax - dwmin),
-                           static_cast<uint32_t>(16 + dhmax - dhmin), 1};
+                           static_cast<uint32_t>((swap ? 32 : 16) + dhmax - dhmin), 1};
         rc = encode_tmap_bf16(&p.amap[0], static_cast<const uint8_t*>(a) + vw.offset * 2, 4, dims, str, box, 128);
         if (rc != VQB_OK) return rc;
     }
@@ -845,7 +958,7 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         const uint64_t ktot = static_cast<uint64_t>(d->ntaps) * d->C;
         uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->Cout)};
         uint64_t str[1] = {ktot * 2};
-        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(swap ? 128 : block_n)};
         rc = encode_tmap_bf16(&p.bmap, w_packed, 2, dims, str, box, 128);
         if (rc != VQB_OK) return rc;
     }

@@ -302,30 +302,34 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const 
         const int p0 = blockIdx.x * pix_per_chunk;
         const int p1 = min(HW, p0 + pix_per_chunk);
         const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
-        for (int p = p0 + pr; p < p1; p += 2 * R) {
-            const bool two = (p + R) < p1;
-            uint4 ux0 = ldg16(x + base + static_cast<int64_t>(p) * C);
-            uint4 ud0 = ldg16(dy + base + static_cast<int64_t>(p) * C);
-            uint4 ux1 = two ? ldg16(x + base + static_cast<int64_t>(p + R) * C) : make_uint4(0, 0, 0, 0);
-            uint4 ud1 = two ? ldg16(dy + base + static_cast<int64_t>(p + R) * C) : make_uint4(0, 0, 0, 0);
+        // 4 pixel rows (8 x 16-byte loads) in flight per thread: with 2 rows the kernel sat at 57 % of HBM bandwidth on
+        // load latency (ncu: 16 warps/SM, long-scoreboard stalls)
+        for (int p = p0 + pr; p < p1; p += 4 * R) {
+            uint4 ux[4], ud[4];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-            if (k == 1 && !two) break;
-            float f[8], d[8];
-            cvt8(k ? ux1 : ux0, f);
-            cvt8(k ? ud1 : ud0, d);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (f[j] - mean[j]) * rstd[j];
-                float du = d[j];
-                if (silu) {
-                    const float u = fmaf(xh, ga[j], be[j]);
-                    const float sg = sigmoidf_(u);
-                    du *= sg * (1.f + u * (1.f - sg));
-                }
-                s1[j] += du;
-                s2[j] += du * xh;
+            for (int k = 0; k < 4; ++k) {
+                const bool in = (p + k * R) < p1;
+                ux[k] = in ? ldg16(x + base + static_cast<int64_t>(p + k * R) * C) : make_uint4(0, 0, 0, 0);
+                ud[k] = in ? ldg16(dy + base + static_cast<int64_t>(p + k * R) * C) : make_uint4(0, 0, 0, 0);
             }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if ((p + k * R) >= p1) break;
+                float f[8], d[8];
+                cvt8(ux[k], f);
+                cvt8(ud[k], d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (f[j] - mean[j]) * rstd[j];
+                    float du = d[j];
+                    if (silu) {
+                        const float u = fmaf(xh, ga[j], be[j]);
+                        const float sg = sigmoidf_(u);
+                        du *= sg * (1.f + u * (1.f - sg));
+                    }
+                    s1[j] += du;
+                    s2[j] += du * xh;
+                }
             }
         }
 #pragma unroll
@@ -367,11 +371,13 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ cs, const float
 }
 
 // dx = rstd * (du*gamma - S1 - xhat*S2) (+ add)
-__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                    const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
-                                    const float* __restrict__ mr, const float* __restrict__ gs,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
-                                    int G, int pix_per_chunk, int silu, float* __restrict__ colsum /* [C] or null */) {
+template <bool ADD, int U>
+__global__ void __launch_bounds__(256, 2)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                    const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
+                    const float* __restrict__ mr, const float* __restrict__ gs, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int HW, int C, int G, int pix_per_chunk, int silu,
+                    float* __restrict__ colsum /* [C] or null */) {
     extern __shared__ float sm[];  // [C] (only when colsum != null)
     const int V = C >> 3, R = blockDim.x / V;
     const int cv = threadIdx.x % V, pr = threadIdx.x / V;
@@ -380,61 +386,62 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
         __syncthreads();
     }
     if (pr < R) {
-    const int n = blockIdx.y, cpg = C / G;
-    float mean[8], rstd[8], ga[8], be[8], S1[8], S2[8], cs8[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = cv * 8 + j, g = c / cpg;
-        mean[j] = mr[(n * G + g) * 2];
-        rstd[j] = mr[(n * G + g) * 2 + 1];
-        S1[j] = gs[(n * G + g) * 2];
-        S2[j] = gs[(n * G + g) * 2 + 1];
-        ga[j] = gamma[c];
-        be[j] = beta[c];
-    }
-    const int p0 = blockIdx.x * pix_per_chunk;
-    const int p1 = min(HW, p0 + pix_per_chunk);
-    const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
-    for (int pp = p0 + pr; pp < p1; pp += 2 * R) {
-        const bool two = (pp + R) < p1;
-        const int64_t off0 = base + static_cast<int64_t>(pp) * C, off1 = off0 + static_cast<int64_t>(R) * C;
-        uint4 ux0 = ldg16(x + off0), ud0 = ldg16(dy + off0);
-        uint4 ua0 = add ? ldg16(add + off0) : make_uint4(0, 0, 0, 0);
-        uint4 ux1 = two ? ldg16(x + off1) : make_uint4(0, 0, 0, 0);
-        uint4 ud1 = two ? ldg16(dy + off1) : make_uint4(0, 0, 0, 0);
-        uint4 ua1 = (two && add) ? ldg16(add + off1) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-        if (k == 1 && !two) break;
-        float f[8], d[8], r[8];
-        const int64_t off = k ? off1 : off0;
-        cvt8(k ? ux1 : ux0, f);
-        cvt8(k ? ud1 : ud0, d);
-        cvt8(k ? ua1 : ua0, r);
+        const int n = blockIdx.y, cpg = C / G;
+        float mean[8], rstd[8], ga[8], be[8], S1[8], S2[8], cs8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float xh = (f[j] - mean[j]) * rstd[j];
-            float du = d[j];
-            if (silu) {
-                const float u = fmaf(xh, ga[j], be[j]);
-                const float sg = sigmoidf_(u);
-                du *= sg * (1.f + u * (1.f - sg));
-            }
-            float v = rstd[j] * (du * ga[j] - S1[j] - xh * S2[j]);
-            if (add) v += r[j];
-            f[j] = v;
-            // column sums of the bf16 values actually written (= bias gradient of the conv that produced x)
-            cs8[j] += __bfloat162float(__float2bfloat16(v));
+            const int c = cv * 8 + j, g = c / cpg;
+            mean[j] = mr[(n * G + g) * 2];
+            rstd[j] = mr[(n * G + g) * 2 + 1];
+            S1[j] = gs[(n * G + g) * 2];
+            S2[j] = gs[(n * G + g) * 2 + 1];
+            ga[j] = gamma[c];
+            be[j] = beta[c];
+            cs8[j] = 0.f;
         }
-        store8(dx + off, f);
-        }
-    }
-    if (colsum) {
+        const int p0 = blockIdx.x * pix_per_chunk;
+        const int p1 = min(HW, p0 + pix_per_chunk);
+        const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+        // U pixel rows in flight per thread (2 or 3 16-byte loads each): U = 3 without the skip-gradient operand, 2 with it
+        for (int pp = p0 + pr; pp < p1; pp += U * R) {
+            uint4 ux[U], ud[U], ua[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], cs8[j]);
-    }
+            for (int k = 0; k < U; ++k) {
+                const bool in = (pp + k * R) < p1;
+                const int64_t off = base + static_cast<int64_t>(pp + k * R) * C;
+                ux[k] = in ? ldg16(x + off) : make_uint4(0, 0, 0, 0);
+                ud[k] = in ? ldg16(dy + off) : make_uint4(0, 0, 0, 0);
+                if (ADD) ua[k] = in ? ldg16(add + off) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if ((pp + k * R) >= p1) break;
+                float f[8], d[8], r[8];
+                cvt8(ux[k], f);
+                cvt8(ud[k], d);
+                if (ADD) cvt8(ua[k], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (f[j] - mean[j]) * rstd[j];
+                    float du = d[j];
+                    if (silu) {
+                        const float u = fmaf(xh, ga[j], be[j]);
+                        const float sg = sigmoidf_(u);
+                        du *= sg * (1.f + u * (1.f - sg));
+                    }
+                    float v = rstd[j] * (du * ga[j] - S1[j] - xh * S2[j]);
+                    if (ADD) v += r[j];
+                    f[j] = v;
+                    // column sums of the bf16 values actually written (= bias gradient of the conv that produced x)
+                    cs8[j] += __bfloat162float(__float2bfloat16(v));
+                }
+                store8(dx + base + static_cast<int64_t>(pp + k * R) * C, f);
+            }
+        }
+        if (colsum) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], cs8[j]);
+        }
     }
     if (colsum) {
         __syncthreads();
@@ -769,11 +776,18 @@ int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, co
     gn_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(cs, gamma, gsum, dgamma, dbeta, N, C, G, HW);
     const size_t cs_smem = dx_colsum ? C * sizeof(float) : 0;
     if (dx_colsum) VQB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
-    cv_grid(HW, C, N, gn_bwd_apply_kernel, cs_smem, chunks, ppc);
-    gn_bwd_apply_kernel<<<dim3(chunks, N), T, cs_smem, st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
-        static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), mr, gsum, gamma, beta, HW, C, G, ppc,
-        silu, dx_colsum);
+    if (add) {
+        cv_grid(HW, C, N, gn_bwd_apply_kernel<true, 2>, cs_smem, chunks, ppc);
+        gn_bwd_apply_kernel<true, 2><<<dim3(chunks, N), T, cs_smem, st>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
+            static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), mr, gsum, gamma, beta, HW, C, G,
+            ppc, silu, dx_colsum);
+    } else {
+        cv_grid(HW, C, N, gn_bwd_apply_kernel<false, 3>, cs_smem, chunks, ppc);
+        gn_bwd_apply_kernel<false, 3><<<dim3(chunks, N), T, cs_smem, st>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), nullptr,
+            static_cast<__nv_bfloat16*>(dx), mr, gsum, gamma, beta, HW, C, G, ppc, silu, dx_colsum);
+    }
     VQB_CUDA(cudaGetLastError());
     count_launch(3);
     return VQB_OK;
