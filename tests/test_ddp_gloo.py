@@ -12,23 +12,31 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap, bucket_mb):
     sys.path.insert(0, os.path.join(ROOT, "vqgan-training_b200"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      VQB_OFFLINE="1")
+                      VQB_OFFLINE="1", VQB_DDP_OVERLAP=overlap, VQB_DDP_BUCKET_MB=bucket_mb)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import vae_trainer as vt
 
     torch.manual_seed(100 + rank)  # different init per rank: the wrapper must broadcast rank 0's weights
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     ddp = vt.FlatAllReduceDDP(net)
+    assert (ddp._buckets is not None) == (overlap == "1")
+    if overlap == "1" and float(bucket_mb) < 1e-3:
+        assert len(ddp._buckets) > 1  # the tiny bucket size must split the 4 parameters over several buckets
     w0 = [p.detach().clone() for p in net.parameters()]
     g = torch.Generator().manual_seed(7 + rank)
     x = torch.randn(4, 6, generator=g)
+    # the rank-local gradient, from an unwrapped twin (with overlap on, p.grad is already being averaged after backward)
+    import copy
+    twin = copy.deepcopy(net)
+    yt = twin(x)
+    (vt.gradnorm(yt, 0.5).pow(2).sum() * (rank + 1)).backward()
+    local = [p.grad.detach().clone() for p in twin.parameters()]
     y = ddp.module(x)  # calling .module directly, like the reference loop does (vae_trainer.py:538,624)
     loss = vt.gradnorm(y, 0.5).pow(2).sum() * (rank + 1)
     loss.backward()
-    local = [p.grad.detach().clone() for p in net.parameters()]
     ddp.allreduce_grads()
     avg = [p.grad.detach().clone() for p in net.parameters()]
     s = vt.avg_scalar_over_nodes(float(rank + 1), "cpu")
@@ -41,11 +49,12 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_flat_allreduce_gradnorm_world2():
+@pytest.mark.parametrize("overlap,bucket_mb", [("1", "0.00005"), ("1", "64"), ("0", "64")])
+def test_flat_allreduce_gradnorm_world2(overlap, bucket_mb):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 200)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 200) + {"0.00005": 0, "64": 1}[bucket_mb] + 2 * int(overlap)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap, bucket_mb)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])

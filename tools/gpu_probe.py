@@ -639,6 +639,69 @@ def group_halobench():
     return True
 
 
+def group_wgbench():
+    """weight-gradient GEMM: split-K sweep per shape, 256-row tiles (default) vs 128-row tiles (debug bit 64)"""
+    import ops
+    for (N, H, W, Ci, Co) in [(32, 32, 32, 512, 512), (32, 256, 256, 128, 128), (32, 64, 64, 512, 512),
+                              (32, 128, 128, 256, 256)]:
+        g = plans.geom_s1(N, H, W, Ci, 3)
+        ks0 = ops.choose_ksplit(g, Co)
+        print(f"-- {Ci}->{Co} @ {H}x{W}: choose_ksplit = {ks0}")
+        for mode in (0, 64):
+            L.vqb_set_debug_mode(mode)
+            for ks in sorted({max(1, ks0 // 2), ks0, ks0 * 2, 4, 16}):
+                print(f"[dbg={mode}]", end=" ")
+                bench_wgrad(N, H, W, Ci, Co, 3, ks)
+        L.vqb_set_debug_mode(0)
+    return True
+
+
+def group_tinybench():
+    """first / last layers (3 -> 128 fat-pixel conv, 128 -> 3 NCHW fp32 conv) at 256^2, N=32: fwd and fwd+bwd time"""
+    import ops
+    torch.manual_seed(0)
+    N, H = 32, 256
+    x = (torch.rand(N, 3, H, H, device=dev) - 0.5)
+    wt = ((torch.rand(128, 3, 3, 3, device=dev) - 0.5) * 0.5).requires_grad_(True)
+    b = rnd(128).requires_grad_(True)
+    cache = ops.PackedCache()
+    xa = ops.to_nhwc(x, None, None, True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, tag, iters=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"BENCH {tag}: {e0.elapsed_time(e1) / iters:.3f} ms", flush=True)
+
+    with torch.no_grad():
+        timeit(lambda: ops.conv(xa, wt, b, cache, "fat3"), "conv_in 3->128 fat3 fwd")
+    gy = rnd(N, H, H, 128).to(torch.bfloat16)
+
+    def fb():
+        y = ops.conv(xa, wt, b, cache, "fat3")
+        y.backward(gy)
+    timeit(fb, "conv_in 3->128 fat3 fwd+bwd (wgrad only)")
+    h = rnd(N, H, H, 128).to(torch.bfloat16).requires_grad_(True)
+    w2 = (rnd(3, 128, 3, 3) * 0.03).requires_grad_(True)
+    b2 = rnd(3).requires_grad_(True)
+    c2 = ops.PackedCache()
+    with torch.no_grad():
+        timeit(lambda: ops.conv(h, w2, b2, c2, "s1", nchw_out=True), "conv_out 128->3 nchw fwd")
+    g2 = rnd(N, 3, H, H)
+
+    def fb2():
+        y = ops.conv(h, w2, b2, c2, "s1", nchw_out=True)
+        y.backward(g2)
+    timeit(fb2, "conv_out 128->3 fwd+bwd (dgrad + wgrad)")
+    return True
+
+
 def group_resbench():
     """epilogue with a residual operand: TMA-prefetched tiles (default) vs per-thread loads (debug bit 512)"""
     for (N, H, W, C) in [(32, 256, 256, 128), (32, 128, 128, 256), (32, 64, 64, 512), (32, 32, 32, 512)]:

@@ -14,6 +14,13 @@ import torch
 import native
 import vae_trainer as vt
 
+RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+if WORLD > 1:  # torchrun: one process per GPU, NCCL
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl")
+    if RANK != 0:
+        sys.stdout = open(os.devnull, "w")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 ch = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 gan = len(sys.argv) > 3 and sys.argv[3] == "gan"
@@ -46,7 +53,8 @@ if os.environ.get("VQB_PROFILE", "0") == "1":
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         tr.step(next(loader)[0])
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("VQB_PROFILE_ROWS", "40")),
+                                    max_name_column_width=70))
 
     from torch.autograd import DeviceType
     evs = [e for e in prof.events() if e.device_type == DeviceType.CUDA]
@@ -71,3 +79,8 @@ if os.environ.get("VQB_PROFILE", "0") == "1":
                 c[name[:60]] += g
         for name, g in c.most_common(15):
             print(f"   idle before {name}: {g / 1e3:.2f} ms")
+
+if WORLD > 1:
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -6,6 +6,9 @@
 //
 // Reference semantics: FP32GroupNorm ae.py:41-53 (32 groups, biased variance, eps inside sqrt,
 // fp32 math), swish ae.py:13-14, Upsample ae.py:157-167 (nearest), Conv2d bias gradients.
+#ifndef VQB_EXACT_SIGMOID
+#define VQB_EXACT_SIGMOID 0
+#endif
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -29,7 +32,18 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
     u.w = pack_bf16x2(f[6], f[7]);
     *reinterpret_cast<uint4*>(p) = u;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// sigmoid(x) = 0.5 + 0.5 tanh(x/2) with the single-instruction MUFU.TANH (abs error of the sigmoid <= ~2.5e-4, an order
+// of magnitude below the bf16 rounding of the activations it multiplies): one SFU op instead of ex2 + rcp. The GroupNorm
+// kernels sit at the SFU / FP32-issue / HBM triple point (ncu: XU 42 %, issue 52 %, DRAM 57 %), so this is time.
+__device__ __forceinline__ float sigmoidf_(float x) {
+#if VQB_EXACT_SIGMOID
+    return 1.f / (1.f + __expf(-x));
+#else
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+#endif
+}
 
 // ------------------------------------------------------------------ weight packing
 // out[r][slot][k] (bf16), r < R, k < Kpad:  transpose ? w[k][r][tap] : w[r][k][tap]   (w is OIHW fp32,

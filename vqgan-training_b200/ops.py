@@ -105,8 +105,10 @@ def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
     bh = p2(g.Ho, kpix // bw)
     bn = kpix // (bw * bh)
     boxes = -(-g.Wo // bw) * -(-g.Ho // bh) * -(-g.N // bn)
-    # pick the split count whose (tile, split) unit count fills whole waves of 148 persistent CTAs best (a 2.2-wave
-    # launch runs as long as a 3-wave one), with >= 4 K-blocks per unit and a bounded fp32 partial buffer
+    # pick the split count whose (tile, split) unit count best fills ONE wave of 148 persistent CTAs: every unit pays a
+    # fixed pipeline-fill + fp32-partial-tile epilogue, and the reduction kernel reads ksplit partials, so a single
+    # full wave beats two (measured, tools/gpu_probe.py wgbench: 512->512 @ 32^2 ks=4 1471 vs ks=8 1305 TFLOP/s;
+    # 128->128 @ 256^2 ks=24 1052 vs ks=49 978; 256->256 @ 128^2 ks=16 1598 vs ks=32 1456)
     sms = 148
     max_ks = max(1, min(boxes // 4, 128, (256 << 20) // max(1, Cout_pad * cols * 4)))
     best, best_score = 1, -1.0
@@ -114,8 +116,7 @@ def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
         units = tiles * ks
         waves = -(-units // sms)
         eff = units / (waves * sms)
-        # mild preference for >= 2 waves (hides the per-unit prologue/epilogue) and against needless splitting
-        score = eff - (0.08 if waves < 2 else 0.0) - 0.002 * ks
+        score = eff - 0.06 * (waves - 1) - 0.0005 * ks
         if score > best_score:
             best, best_score = ks, score
     return best

@@ -197,9 +197,18 @@ def cleanup():
 
 class FlatAllReduceDDP(nn.Module):
     """Data-parallel wrapper with the DDP surface the reference uses (`.module`, `module.`-prefixed state_dict,
-    constructor broadcast from rank 0) whose gradient averaging is an explicit flat NCCL all-reduce issued after
-    backward (`allreduce_grads`) — it therefore also covers the `vae.module.encoder(...)` calling style that
-    bypasses DDP.forward in the reference."""
+    constructor broadcast from rank 0) whose gradient averaging is explicit — it therefore also covers the
+    `vae.module.encoder(...)` calling style that bypasses DDP.forward in the reference.
+
+    VQB_DDP_OVERLAP=1 (opt-in): parameters are grouped, in reverse registration order (~ the order backward produces
+    their gradients), into flat fp32 buckets of VQB_DDP_BUCKET_MB (64) MiB. A post-accumulate-grad hook copies each
+    finished gradient into its bucket slot (the slot then IS `param.grad`) and, when a bucket is complete, launches its
+    NCCL all-reduce(AVG) asynchronously, so the transfer runs under the rest of backward; `allreduce_grads()` after
+    backward only waits. Requires one backward per `allreduce_grads()` call (what the training step does).
+    Default (VQB_DDP_OVERLAP=0): one flat all-reduce issued by `allreduce_grads()` after backward. Measured at N=2
+    (B=32/GPU): 100.4 ms/step flat vs 100.9 ms bucketed-overlapped vs 98.6 ms on one GPU — the persistent 148-CTA conv
+    kernels own every SM's shared memory, so an NCCL kernel launched mid-backward cannot co-reside and the overlap buys
+    nothing; the flat form stays the default."""
 
     def __init__(self, module: nn.Module, device_ids=None):
         super().__init__()
@@ -208,15 +217,70 @@ class FlatAllReduceDDP(nn.Module):
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, 0)
         self._flat = None
+        self._buckets = None
+        self._where = {}
+        if _dist_on() and os.environ.get("VQB_DDP_OVERLAP", "0") == "1":
+            self._build_buckets(float(os.environ.get("VQB_DDP_BUCKET_MB", "64")))
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
+
+    def _build_buckets(self, bucket_mb: float):
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        cap = max(1, int(bucket_mb * (1 << 20) / 4))
+        groups, cur, n = [], [], 0
+        for p in reversed(params):
+            cur.append(p)
+            n += p.numel()
+            if n >= cap:
+                groups.append(cur)
+                cur, n = [], 0
+        if cur:
+            groups.append(cur)
+        self._buckets = []
+        for grp in groups:
+            flat = torch.zeros(sum(p.numel() for p in grp), device=grp[0].device, dtype=torch.float32)
+            views, off = [], 0
+            for p in grp:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            bk = {"params": grp, "flat": flat, "views": views, "ready": 0, "work": None}
+            for i, p in enumerate(grp):
+                self._where[p] = (bk, i)
+                p.register_post_accumulate_grad_hook(self._grad_ready)
+            self._buckets.append(bk)
+
+    @torch.no_grad()
+    def _grad_ready(self, p):
+        bk, i = self._where[p]
+        if bk["work"] is not None:
+            raise RuntimeError("FlatAllReduceDDP: a second backward reached a bucket that is already being reduced; "
+                               "call allreduce_grads() after every backward or set VQB_DDP_OVERLAP=0")
+        v = bk["views"][i]
+        if p.grad is not v:
+            v.copy_(p.grad)
+            p.grad = v  # the optimizer reads the averaged gradient straight from the bucket
+        bk["ready"] += 1
+        if bk["ready"] == len(bk["params"]):
+            bk["work"] = dist.all_reduce(bk["flat"], op=dist.ReduceOp.AVG, async_op=True)
 
     @torch.no_grad()
     def allreduce_grads(self):
         if not _dist_on():
             return
-        params = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
+        if self._buckets is not None:
+            rest = [p for p in self.module.parameters()
+                    if p.requires_grad and p.grad is not None and p not in self._where]
+            for bk in self._buckets:
+                if bk["ready"] == 0:
+                    continue  # no gradient reached this bucket in this step (same on every rank)
+                if bk["work"] is None:  # some parameters of the bucket were unused: reduce what is there
+                    bk["work"] = dist.all_reduce(bk["flat"], op=dist.ReduceOp.AVG, async_op=True)
+                bk["work"].wait()
+                bk["work"], bk["ready"] = None, 0
+            params = rest
+        else:
+            params = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
         if not params:
             return
         n = sum(p.numel() for p in params)
