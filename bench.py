@@ -179,7 +179,12 @@ def profile_conv_kernels(tr, batch_dev):
     rec = {"conv": [], "wgrad": []}
     orig_conv, orig_wgrad = ops.run_conv_gemm, ops.run_wgrad
 
+    def is_fat(g):  # fat-pixel first/last layer: 64-wide K runs carrying 3 real taps x 8 channels (3 real) each
+        return g.C == 64 and len(g.taps) == 3 and len(g.views) == 1 and g.views[0].sw == 8
+
     def flops_conv(g, Cout):
+        if is_fat(g):
+            return 2.0 * g.N * g.Ho * g.Wo * Cout * 27
         return 2.0 * g.N * g.Ho * g.Wo * Cout * g.C * len(g.taps)
 
     def conv_wrap(g, a, wp, Cout, out, out_strides, *aa, **kk):
@@ -200,7 +205,7 @@ def profile_conv_kernels(tr, batch_dev):
         r = orig_wgrad(g, x, dy, weight_shape, Cout_pad, **kk)
         e1.record()
         Cout, Cin, KH, KW = weight_shape
-        if g.C == 24 and len(g.taps) == 3:  # fat-pixel first layer: 3 real channels x 9 taps, not the padded 24 x 3
+        if is_fat(g):  # 3 real channels x 9 taps, not the padded 64 x 3
             Cin, KH, KW = 3, 3, 3
         rec["wgrad"].append((e0, e1, 2.0 * g.N * g.Ho * g.Wo * Cout * Cin * KH * KW,
                              ("wgrad", g.N, g.Ho, g.Wo, g.C, Cout, len(g.taps), len(g.views))))

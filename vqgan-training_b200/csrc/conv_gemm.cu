@@ -775,8 +775,11 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     // Halo mode: one dense view, taps = shifts within a <= 3x3 window, 64-channel chunks, staged bf16 NHWC output.
     // Tile = 16 x 16 output pixels of one image (two 8 x 16 sub-tiles side by side) x 128 output channels.
     // (Cout < 128: 64-column MMAs are issue/smem bound either way and the per-tap path measured ~10 % faster)
+    //  Cout <= 32 (decoder conv_out, data gradients of 3-channel layers; any output format, direct-store epilogue): the
+    //  nine-fold L2->SM re-read of the activations is all there is to save, so the halo wins there too)
+    const bool halo_big = d->oc == 1 && !d->out_f32 && d->Cout % 16 == 0 && d->Cout >= 128 && !(p_dbg & 256);
     bool halo = !(p_dbg & 1024) && d->nviews == 1 && d->ntaps >= 2 && d->C % 64 == 0 && d->W > 8 && d->H > 8 &&
-                d->oc == 1 && !d->out_f32 && d->Cout % 16 == 0 && d->Cout >= 128 && !(p_dbg & 256);
+                (halo_big || d->Cout <= 32);
     int dwmin = 0, dwmax = 0, dhmin = 0, dhmax = 0;
     if (halo) {
         dwmin = dwmax = d->taps[0].dw;

@@ -210,7 +210,7 @@ class ToNHWC(torch.autograd.Function):
         N, C, H, W = x.shape
         Cp = plans.cpad(C)
         if frame:  # zero-framed [N, H+2, W+2, Cp] for the "fat pixel" first-layer conv
-            y = torch.zeros(N, H + 2, W + 2, Cp, device=x.device, dtype=torch.bfloat16)
+            y = alloc_framed(N, H, W, Cp, x.device)
             check(_L().vqb_nchw_to_nhwc_pad(ptr(x), ptr(y), N, C, H, W, Cp, 1, ptr(shift), ptr(inv_scale),
                                             stream_ptr()), "nchw_to_nhwc_pad")
         else:
@@ -233,6 +233,28 @@ class ToNHWC(torch.autograd.Function):
             check(_L().vqb_nhwc_to_nchw(ptr(gy), ptr(gx), N, C, H, W, Cp, ptr(ctx.inv_scale), stream_ptr()),
                   "nhwc_to_nchw")
         return gx, None, None, None
+
+
+def alloc_framed(N, H, W, C, device) -> torch.Tensor:
+    """Zeroed [N, H+2, W+2, C] bf16 buffer followed by 64 elements of zeroed slack (fat-pixel K runs read up to 5 pixels
+    past the last one; they meet zero weights but must stay inside the allocation and finite)."""
+    n = N * (H + 2) * (W + 2) * C
+    return torch.zeros(n + 64, device=device, dtype=torch.bfloat16)[:n].view(N, H + 2, W + 2, C)
+
+
+def _fat_weights(cache: "PackedCache", weight, key, tapmap, transpose, Kpad):
+    """[R][9 slots][8] packing -> [R][3][64]: columns kw*8 + c of each kh row, zero beyond 24 (plans.geom_fat3)."""
+    ver = (weight._version, weight.data_ptr())
+    k64 = tuple(key) + ("k64",)
+    ent = cache._store.get(k64)
+    if ent is None or ent[0] != ver:
+        wp = cache.get(weight, key, tapmap, transpose, Kpad)
+        R = wp.shape[0]
+        w64 = torch.zeros(R, 3, plans.FAT_K, device=wp.device, dtype=wp.dtype)
+        w64[:, :, :24] = wp.view(R, 3, 24)
+        ent = (ver, w64)
+        cache._store[k64] = ent
+    return ent[1]
 
 
 _fat_state = {"ok": None}
@@ -318,7 +340,10 @@ class ConvFn(torch.autograd.Function):
             g = cache.geom(("f", N, H, W), lambda: plans.geom_patch(N, H, W, Cp, KH))
         else:
             raise ValueError(kind)
-        wp = cache.get(weight, ("fwd", kind), g.tapmap, False, Cp)
+        if kind == "fat3":
+            wp = _fat_weights(cache, weight, ("fwd", kind), g.tapmap, False, Cp)
+        else:
+            wp = cache.get(weight, ("fwd", kind), g.tapmap, False, Cp)
         Cop = plans.cpad(Cout)
         ctx.HW = (H, W)
         b = None
@@ -364,7 +389,7 @@ class ConvFn(torch.autograd.Function):
                 # tiny-Cout conv (decoder conv_out): keep dy in a zero-framed buffer so that the data gradient runs as a
                 # 3-tap fat-pixel conv (24-wide K runs) instead of 9 taps of 8 channels
                 dy_framed = True
-                dy = torch.zeros(N, g.Ho + 2, g.Wo + 2, Cop, device=x.device, dtype=torch.bfloat16)
+                dy = alloc_framed(N, g.Ho, g.Wo, Cop, x.device)
                 check(_L().vqb_nchw_to_nhwc_pad(ptr(gn), ptr(dy), N, Cout, g.Ho, g.Wo, Cop, 1, 0, 0, stream_ptr()),
                       "nchw_to_nhwc_pad")
             else:
@@ -386,7 +411,7 @@ class ConvFn(torch.autograd.Function):
             elif dy_framed:
                 gx = gx_alloc(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
                 gdf = cache.geom(("dfat", N, H, W), lambda: plans.geom_fat3(N, H, W, dgrad=True))
-                wpd = cache.get(weight, ("dgrad", "fat3"), gdf.tapmap, True, Cop)
+                wpd = _fat_weights(cache, weight, ("dgrad", "fat3"), gdf.tapmap, True, Cop)
                 run_conv_gemm(gdf, dy, wpd, Cin, gx, plans.nhwc_strides(H, W, Cp), mask=mask)
             else:
                 gx = gx_alloc(N, H, W, Cp, device=x.device, dtype=torch.bfloat16)
@@ -414,8 +439,8 @@ class ConvFn(torch.autograd.Function):
                                       out_ptr_offset_bytes=(kh * W + kw) * Cp * 2, mask=mask)
         if ctx.needs_input_grad[1]:
             if kind == "fat3":  # [Cout][kw*8 + c][kh] -> OIHW
-                g3 = run_wgrad(g, x, dy, (Cout, 24, 3, 1), Cop)
-                gw = g3.view(Cout, 3, 8, 3)[:, :, :Cin, :].permute(0, 2, 3, 1).contiguous()
+                g3 = run_wgrad(g, x, dy, (Cout, plans.FAT_K, 3, 1), Cop)  # [Cout][kw*8 + c (24 real of 64)][kh]
+                gw = g3[:, :24, :, 0].reshape(Cout, 3, 8, 3)[:, :, :Cin, :].permute(0, 2, 3, 1).contiguous()
             elif dy_framed:
                 gw = run_wgrad(g, x, dy, weight.shape, Cop,
                                dy_view=plans.framed_interior_view(N, g.Ho, g.Wo, Cop))

@@ -151,16 +151,21 @@ def geom_up_dgrad(N, h, w, Cop) -> ConvGeom:
 
 
 # ---- first-layer "fat pixel" 3x3 conv over an 8-channel image ------------------------------------------------------
-# The image lives in a zero-framed buffer [N][H+2][W+2][8]; three horizontally adjacent pixels are 24 CONTIGUOUS elements,
-# so the conv becomes 3 taps (kh) of K = 24 instead of 9 taps of K = 8: a third of the TMA requests on a layer that is
-# purely TMA-request bound (K = 8 real channels per 128-byte row). Weights [Cout][kh][kw*8 + c] are the ordinary
-# [Cout][9][8] packing read with a different stride.
+# The image lives in a zero-framed buffer [N][H+2][W+2][8]; horizontally adjacent pixels are CONTIGUOUS, so the conv
+# becomes 3 taps (kh) whose K run starts at pixel (w-1) and covers the 8 pixels w-1..w+6 = 64 elements = one full
+# 128-byte K chunk: columns 0..23 carry the three real taps (kw*8 + c), columns 24..63 meet ZERO weights. The run is 64
+# wide (not 24) on purpose: ncu showed the TMA unit spending ~28 cycles per row when the box's inner dimension is
+# partly out of range (24 of 64: 640 us for a layer whose HBM floor is 90 us); a fully in-range 128-byte row costs ~1.
+# The buffer carries 64 elements of zeroed slack so the last rows stay inside the allocation.
+FAT_K = 64
+
+
 def fat_view(N, H, W) -> VqbView:
     return VqbView(offset=0, Wv=W, Hv=H + 2, Nv=N, _pad=0, sw=8, sh=(W + 2) * 8, sn=(H + 2) * (W + 2) * 8)
 
 
 def geom_fat3(N, H, W, dgrad=False) -> ConvGeom:
-    g = ConvGeom(N, H, W, 24, [fat_view(N, H, W)])
+    g = ConvGeom(N, H, W, FAT_K, [fat_view(N, H, W)])
     for kh in range(3):
         g.taps.append((0, 0, kh))
     g.tapmap = [8 - t for t in range(9)] if dgrad else list(range(9))  # 9 packed slots of 8 = 3 fat taps of 24
