@@ -554,14 +554,16 @@ def group_conv():
     ok &= case_conv(8, 64, 64, 128, 128, 3, mask=True)
     ok &= case_conv(2, 20, 20, 64, 96, 3, bias=True, res=True, mask=True)
     ok &= case_conv(5, 12, 12, 64, 64, 3, mask=True, relu=True)
-    # Cout = 128, H >= 32 with the experimental swap mode (debug bit 4096: weights as the M operand, transposed epilogue)
-    # and without it: ragged tiles, every epilogue operand
-    for mode in (4096, 0):
+    # Cout = 128, H >= 32 with the experimental swap mode (debug bit 4096: weights as the M operand, transposed epilogue),
+    # the experimental CTA-pair mode (debug bit 8192: cta_group::2, M = 256 MMAs) and without either: ragged tiles, every
+    # epilogue operand
+    for mode in (4096, 8192, 0):
         L.vqb_set_debug_mode(mode)
         ok &= case_conv(3, 40, 20, 128, 128, 3, bias=True, res=True, relu=True)
         ok &= case_conv(2, 48, 24, 64, 128, 3, bias=True, mask=True)
         ok &= case_conv(9, 64, 64, 256, 128, 3, bias=True)
         ok &= case_conv(4, 128, 128, 128, 128, 3, res=True)
+        ok &= case_conv(2, 32, 32, 128, 128, 3, bias=True)
     L.vqb_set_debug_mode(0)
     return ok
 
@@ -629,7 +631,9 @@ def group_halobench():
     for (N, H, W, Ci, Co) in [(32, 256, 256, 128, 128), (32, 128, 128, 256, 256), (32, 64, 64, 512, 512),
                               (32, 32, 32, 512, 512), (32, 16, 16, 512, 512), (32, 128, 128, 128, 256),
                               (32, 256, 256, 64, 64)]:
-        for mode in (0, 1024):
+        for mode in (0, 8192, 1024):  # default halo mode, CTA-pair mode, one TMA box per tap
+            if mode == 8192 and Co != 128:
+                continue
             L.vqb_set_debug_mode(mode)
             print(f"[dbg={mode}]", end=" ")
             bench_conv(N, H, W, Ci, Co, 3, cudnn=(mode == 1024))

@@ -22,7 +22,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per stage
 constexpr int kThreads = 256;                   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 
 struct alignas(64) ConvParams {
     CUtensorMap amap[VQB_MAX_VIEWS];
@@ -50,6 +50,11 @@ struct alignas(64) ConvParams {
     // each MMA is M128 x N256 (96 B/clk of shared-memory operand reads instead of the 128 B/clk of an N = 128 MMA);
     // the accumulator is [channel lane][pixel column] and the epilogue transposes through the staging tiles.
     int32_t swap, epi_bytes;
+    // pair mode (halo mode, Cout == 128): two CTAs of a cluster form a cta_group::2 pair. Each owns one 8 x 16 sub-tile
+    // (its own halo tile and TMEM accumulator) and HALF of every weight tile; the leader issues M = 256 MMAs. Per SM an
+    // MMA then reads 4 KB of activations + 2 KB of weights per 64 cycles (96 B/clk) instead of the 128 B/clk of two
+    // independent N = 128 streams, which is the measured limiter of the 128-channel layers.
+    int32_t pair, tps;  // tps: taps (weight tiles) per ring stage in halo mode (1, or 3 in pair mode)
     int64_t on, oh, ow, oc;
     void* out;
     const void* res;
@@ -58,20 +63,29 @@ struct alignas(64) ConvParams {
     float* stats;
 };
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
+    // PAIR is a template parameter: cta_group::2 / cluster instructions make a kernel require a cluster launch, so
+    // they may only exist in the instantiation that is launched with cluster dimension 2
+    constexpr bool pair = PAIR;
+    uint32_t crank = 0u;  // 0 = leader of the CTA pair
+    if constexpr (PAIR) crank = cluster_ctarank();
+    const int tile0 = pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tstep = pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int wsh = pair ? static_cast<int>(crank) * 8 : 0;  // this CTA's sub-tile inside the pair's 16-wide tile
 
     // carve shared memory (1024-B aligned for the 128B swizzle atoms)
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t stages = p.stages;
     const uint32_t a_bytes = static_cast<uint32_t>(p.mtiles) * kABytes;
-    const uint32_t b_bytes = static_cast<uint32_t>(p.swap ? 128 : p.block_n) * kBlockK * 2;
+    const uint32_t b_bytes = static_cast<uint32_t>(p.swap ? 128 : (p.pair ? p.block_n / 2 : p.block_n)) * kBlockK * 2;
     const uint32_t mtiles = p.mtiles, nbuf = p.nbuf;
     uint8_t* sA = base;  // halo mode: h_stages halo tiles; else `stages` 128-row tap tiles
     uint8_t* sB = base + (p.halo ? static_cast<uint32_t>(p.h_stages * p.h_bytes) : stages * a_bytes);
-    uint8_t* sOut = sB + stages * b_bytes;  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
+    uint8_t* sOut = sB + stages * b_bytes * static_cast<uint32_t>(p.tps);  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
     float* sStat = reinterpret_cast<float*>(sOut + 2 * 16384);  // [4 warps][64 ch][2] (GroupNorm statistics combine)
     uint8_t* sAux = sOut + 2 * 16384 + 2048;  // 2 x 16 KB residual / mask tiles (same swizzled layout as sOut)
     uint64_t* full = reinterpret_cast<uint64_t*>(sOut + p.epi_bytes);
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&tempty[i], pair ? 256 : 128);  // pair: the leader's barrier collects both CTAs' epilogues
         }
         mbar_init(&afull[0], 1);
         mbar_init(&afull[1], 1);
@@ -111,11 +125,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, p.tmem_cols);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_pair(tmem_slot, p.tmem_cols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, p.tmem_cols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR)
+        cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled on them
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -129,17 +151,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint8_t* b_dst = sB;
         uint8_t* h_dst = sA;
         const uint32_t h_tx = static_cast<uint32_t>(p.h_tx);
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
             const int n_tile = tile % p.n_tiles;
             const int m_tile = tile / p.n_tiles;
             const int tw = m_tile % p.tiles_w;
             const int th = (m_tile / p.tiles_w) % p.tiles_h;
             const int tn = m_tile / (p.tiles_w * p.tiles_h);
-            const int w0 = (tw << p.lbw) + p.h_w0, h0 = (th << p.lbh) + p.h_h0;
-            const int ncol0 = n_tile * p.block_n;
+            const int w0 = (tw << p.lbw) + p.h_w0 + wsh, h0 = (th << p.lbh) + p.h_h0;
+            const int ncol0 = n_tile * p.block_n + (pair ? static_cast<int>(crank) * 64 : 0);
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 mbar_wait(&hempty[hs], hph ^ 1);
-                if ((p.dbg & 3) == 1) {
+                if constexpr (PAIR) {
+                    // both CTAs' boxes complete on the LEADER's barrier (which expects the bytes of both)
+                    if (crank == 0) mbar_arrive_expect_tx(&hfull[hs], 2 * h_tx);
+                    tma_load_4d_pair(&p.amap[0], mapa_u32(smem_u32(&hfull[hs]), 0), h_dst, kc * kBlockK, w0, h0, tn);
+                } else if ((p.dbg & 3) == 1) {
                     mbar_arrive(&hfull[hs]);
                 } else {
                     mbar_arrive_expect_tx(&hfull[hs], h_tx);
@@ -153,9 +179,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     h_dst += p.h_bytes;
                 }
                 int kcol = kc * kBlockK;
-                for (int t = 0; t < p.ntaps; ++t, kcol += p.C) {
+                const int tps = p.tps;
+                for (int t = 0; t < p.ntaps; t += tps, kcol += tps * p.C) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    if ((p.dbg & 3) == 1) {
+                    if constexpr (PAIR) {
+                        // one ring stage = tps weight tiles (both CTAs' halves complete on the leader's barrier)
+                        if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * b_bytes * tps);
+                        const uint32_t fa = mapa_u32(smem_u32(&full[stage]), 0);
+                        for (int j = 0; j < tps; ++j)
+                            tma_load_2d_pair(&p.bmap, fa, b_dst + j * b_bytes, kcol + j * p.C, ncol0);
+                    } else if ((p.dbg & 3) == 1) {
                         mbar_arrive(&full[stage]);
                     } else {
                         mbar_arrive_expect_tx(&full[stage], b_bytes);
@@ -166,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         phase ^= 1;
                         b_dst = sB;
                     } else {
-                        b_dst += b_bytes;
+                        b_dst += b_bytes * tps;
                     }
                 }
             }
@@ -177,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint8_t* a_dst = sA;
         uint8_t* b_dst = sB;
         const uint32_t tx_bytes = a_bytes + b_bytes;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tile_iter) {
             const int n_tile = tile % p.n_tiles;
             const int m_tile = tile / p.n_tiles;
             const int tw = m_tile % p.tiles_w;
@@ -215,11 +248,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer (single thread) =====================
+    } else if (warp == 1 && lane == 0 && crank == 0) {
+        // ===================== MMA issuer (single thread; in pair mode only the leader CTA's) =====================
         // This thread must issue 4*mtiles MMAs per K-block in well under the ~512*mtiles cycles the tensor core needs
         // for them: descriptors are base + increments (no divisions, no per-K-block descriptor builds).
-        const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(pair ? 2 * kBlockM : kBlockM, p.block_n, 0, 0);
         const uint64_t da_base = make_smem_desc(smem_u32(sA), 0, 1024, 2);
         const uint64_t db_base = make_smem_desc(smem_u32(sB), 0, 1024, 2);
         const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;  // descriptor address field is (addr >> 4)
@@ -227,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const bool do_mma = (p.dbg & 3) != 2;
         uint32_t stage = 0, phase = 0, a_off = 0, b_off = 0, hstage = 0, hphase = 0;
         uint32_t buf = 0, bpar = 0;  // next TMEM accumulator buffer and the parity of its use count
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
             const uint32_t b0 = buf;
             mbar_wait(&tempty[buf], bpar ^ 1);  // epilogue has drained the previous use of this buffer
             if (++buf == nbuf) {
@@ -256,11 +289,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&hfull[hstage], hphase);
                     const uint64_t dah = dh_base + hstage * h_step;
-                    for (int t = 0; t < p.ntaps; ++t) {
+                    const int tps = p.tps;
+                    for (int t = 0; t < p.ntaps; t += tps) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint64_t da = dah + p.tap_off16[t], db = db_base + b_off;
-                        if (do_mma && p.swap) {
+                        if constexpr (PAIR) {
+                            for (int j = 0; j < tps; ++j) {
+                                const uint64_t daj = dah + p.tap_off16[t + j], dbj = db + j * b_step;
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16_pair(d0, daj + 2 * k, dbj + 2 * k, idesc, (acc | j) | k);
+                            }
+                            umma_commit_pair(&empty[stage], 3);
+                        } else if (do_mma && p.swap) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d0, db + 2 * k, da + 2 * k, idesc, acc | k);
                         } else if (do_mma) {
@@ -272,17 +314,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                     umma_bf16(d1, da + mt_off + 2 * k, db + 2 * k, idesc, acc | k);
                             }
                         }
-                        umma_commit(&empty[stage]);
+                        if (!pair) umma_commit(&empty[stage]);
                         acc = 1;
                         if (++stage == stages) {
                             stage = 0;
                             phase ^= 1;
                             b_off = 0;
                         } else {
-                            b_off += b_step;
+                            b_off += b_step * tps;
                         }
                     }
-                    umma_commit(&hempty[hstage]);  // every tap of this chunk has been issued: the halo tile may be refilled
+                    // every tap of this chunk has been issued: the halo tile may be refilled
+                    if constexpr (PAIR)
+                        umma_commit_pair(&hempty[hstage], 3);
+                    else
+                        umma_commit(&hempty[hstage]);
                     if (++hstage == static_cast<uint32_t>(p.h_stages)) {
                         hstage = 0;
                         hphase ^= 1;
@@ -314,8 +360,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     b_off += b_step;
                 }
             }
-            umma_commit(&tfull[b0]);  // accumulator(s) complete -> epilogue
-            if (two) umma_commit(&tfull[b1]);
+            if constexpr (PAIR) {
+                umma_commit_pair(&tfull[b0], 3);  // both CTAs' epilogues drain their half of the M = 256 accumulator
+            } else {
+                umma_commit(&tfull[b0]);  // accumulator(s) complete -> epilogue
+                if (two) umma_commit(&tfull[b1]);
+            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue (4 warps = 128 accumulator rows) =====================
@@ -336,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const bool aux_tma = p.aux_tma != 0;
             const bool elected = (ew == 0 && lane == 0);
             uint32_t ebuf = 0, epar = 0, step = 0;
-            int ptile = blockIdx.x;
+            int ptile = tile0;
             uint32_t ps = 0, pstep = 0;
             auto aux_issue_next = [&]() {
                 if (ptile >= p.total_tiles) return;
@@ -349,10 +399,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 tma_load_4d(&p.xmap, &afull[pstep & 1u], dst + 16384, 64, tw << 3, (th << 5) + static_cast<int>(ps) * 16, tn);
                 ++pstep;
                 ps ^= 1u;
-                if (ps == 0) ptile += gridDim.x;
+                if (ps == 0) ptile += tstep;
             };
             if (aux_tma && elected) aux_issue_next();  // step 0
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
                 const int tw = tile % p.tiles_w;
                 const int th = (tile / p.tiles_w) % p.tiles_h;
                 const int tn = tile / (p.tiles_w * p.tiles_h);
@@ -424,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         // elected thread walks the same (tile, sub-tile, channel group) sequence one step ahead.
         const bool aux_tma = p.aux_tma != 0;
         const bool elected = (ew == 0 && lane == 0);
-        int ptile = blockIdx.x;
+        int ptile = tile0;
         uint32_t pmt = 0, pq = 0;
         int pcg = 0;
         auto aux_issue_next = [&]() {
@@ -436,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int tn = m_tile / (p.tiles_w * p.tiles_h);
             const int col = n_tile * p.block_n + pcg * 64;
             mbar_arrive_expect_tx(&afull[pq & 1u], 16384u);
-            tma_load_4d(&p.xmap, &afull[pq & 1u], sAux + (pq & 1u) * 16384u, col, (tw << p.lbw) + (pmt ? p.mt_dw : 0),
+            tma_load_4d(&p.xmap, &afull[pq & 1u], sAux + (pq & 1u) * 16384u, col, (tw << p.lbw) + (pmt ? p.mt_dw : 0) + wsh,
                         (th << p.lbh) + (pmt ? p.mt_dh : 0), (tn << p.lbn) + (pmt ? p.mt_dn : 0));
             ++pq;
             ++pcg;
@@ -444,12 +494,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 pcg = 0;
                 if (++pmt == mtiles) {
                     pmt = 0;
-                    ptile += gridDim.x;
+                    ptile += tstep;
                 }
             }
         };
         if (aux_tma && elected) aux_issue_next();  // group 0
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
           const int n_tile = tile % p.n_tiles;
           const int m_tile = tile / p.n_tiles;
           const int tw = m_tile % p.tiles_w;
@@ -471,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 hi = static_cast<int>((row >> 3) & 15u);
                 ni = 0;
             }
-            const int w = (tw << p.lbw) + wi, h = (th << p.lbh) + hi, n = (tn << p.lbn) + ni;
+            const int w = (tw << p.lbw) + wi + wsh, h = (th << p.lbh) + hi, n = (tn << p.lbn) + ni;
             const bool valid = (w < p.W) && (h < p.H) && (n < p.N) && !no_store;
             const int64_t pix = static_cast<int64_t>(n) * p.on + static_cast<int64_t>(h) * p.oh +
                                 static_cast<int64_t>(w) * p.ow;
@@ -483,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 // -------- staged epilogue: registers -> 128B-swizzled smem tile -> one TMA store per 64 channels.
                 // (direct per-thread stores write 32 B per lane at a 2*Cout-byte pitch: measured to cost up to half of the
                 // kernel time on short-K layers)
-                const int ow0 = (tw << p.lbw) + (mt ? p.mt_dw : 0);
+                const int ow0 = (tw << p.lbw) + (mt ? p.mt_dw : 0) + wsh;
                 const int oh0 = (th << p.lbh) + (mt ? p.mt_dh : 0);
                 const int on0 = (tn << p.lbn) + (mt ? p.mt_dn : 0);
                 const uint32_t r = ew * 32 + lane;
@@ -695,7 +745,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[as]);
+            if constexpr (PAIR) {
+                if (crank != 0)
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+                else
+                    mbar_arrive(&tempty[as]);
+            } else {
+                mbar_arrive(&tempty[as]);
+            }
           }
         }
         if (p.tma_store && ew == 0 && lane == 0) bulk_wait_all();  // smem must outlive the last bulk stores
@@ -703,10 +760,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR)
+        cluster_sync_all();  // neither CTA may exit (or free TMEM) while the other still signals into it
+    else
+        __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, p.tmem_cols);
+        if constexpr (PAIR)
+            tmem_dealloc_pair(tmem_base, p.tmem_cols);
+        else
+            tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -802,6 +865,12 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     // N = 256 keeps the MMA's shared-memory operand reads under 128 B/clk (an M128 x N128 x K16 MMA reads 8 KB in its 64
     // cycles: exactly the limit); with 256 columns one 8 x 16 sub-tile per CTA tile leaves room for TMEM double buffering.
     const int halo_mtiles = (d->Cout >= 256 && !(p_dbg & 2048)) ? 1 : 2;
+    // CTA pairs (cta_group::2, M = 256 MMAs, half a weight tile per CTA) for the 128-channel layers: functionally complete
+    // and tested, but measured SLOWER than two independent N = 128 streams (1040 vs 1192 TFLOP/s on 128->128 @ 256^2
+    // with three weight tiles per ring stage; 814 with one) — the single issuing thread now feeds two tensor cores and
+    // every stage hand-off crosses SMs. Opt-in through debug bit 8192 until that is understood.
+    const bool pair = halo && !swap && halo_big && d->Cout == 128 && (p_dbg & 8192);
+    p.pair = pair ? 1 : 0;
     if (swap)
         block_n = 256;  // accumulator columns = pixels
     else if (halo)
@@ -842,8 +911,8 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         bn = bn2;
     }
     if (halo) {
-        mtiles = swap ? 1 : halo_mtiles;
-        bw = 8 * mtiles;
+        mtiles = (swap || pair) ? 1 : halo_mtiles;
+        bw = pair ? 16 : 8 * mtiles;  // pair: the 16-wide tile is split between the two CTAs (8 columns each)
         bh = swap ? 32 : 16;
         bn = 1;
     }
@@ -894,15 +963,18 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     int stages = (227 * 1024 - 1536 - epi_smem) / stage_bytes;
     size_t ring_bytes = 0;
     p.h_bytes = p.h_stages = p.h_sbo = p.h_w0 = p.h_h0 = p.h_tx = 0;
+    p.tps = 1;
     if (halo) {
-        const int P = 8 * mtiles + (dwmax - dwmin), Q = (swap ? 32 : 16) + (dhmax - dhmin);
+        const int P = 8 * mtiles + (dwmax - dwmin), Q = (swap ? 32 : 16) + (dhmax - dhmin);  // per CTA
         p.h_sbo = P * 128;
         p.h_tx = P * Q * 128;
         p.h_bytes = (p.h_tx + 1023) / 1024 * 1024;
-        p.h_stages = 2;
+        p.h_stages = pair ? 4 : 2;  // pair: a chunk is only 9 x 256 MMA cycles, shorter than one halo load's latency
         p.h_w0 = dwmin;
         p.h_h0 = dhmin;
-        const int b_bytes = (swap ? 128 : block_n) * kBlockK * 2;
+        p.tps = (pair && d->ntaps % 3 == 0 && !(p_dbg & 16384)) ? 3 : 1;
+        if (pair) p.h_stages = (p.tps == 3 && aux_tma) ? 3 : 4;
+        const int b_bytes = (swap ? 128 : (pair ? block_n / 2 : block_n)) * kBlockK * 2 * p.tps;  // per ring stage
         stages = (227 * 1024 - 1536 - epi_smem - p.h_stages * p.h_bytes) / b_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
         VQB_CHECK(stages >= 2, "vqb_conv_gemm: halo mode does not fit in shared memory");
@@ -961,7 +1033,7 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         const uint64_t ktot = static_cast<uint64_t>(d->ntaps) * d->C;
         uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->Cout)};
         uint64_t str[1] = {ktot * 2};
-        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(swap ? 128 : block_n)};
+        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(swap ? 128 : (pair ? block_n / 2 : block_n))};
         rc = encode_tmap_bf16(&p.bmap, w_packed, 2, dims, str, box, 128);
         if (rc != VQB_OK) return rc;
     }
@@ -981,11 +1053,31 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     const size_t smem = 1024 + ring_bytes + epi_smem + 512;
     static bool attr_set = false;
     if (!attr_set) {
-        VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VQB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_gemm_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    if (pair) {
+        // one cluster of two CTAs (a cta_group::2 pair on one TPC) per tile stream
+        int pairs = num_sms() / 2;
+        if (pairs > p.total_tiles) pairs = p.total_tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VQB_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, p));
+    } else {
+        conv_gemm_kernel<false><<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    }
     VQB_CUDA(cudaGetLastError());
     count_launch();
     return VQB_OK;
