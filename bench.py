@@ -324,6 +324,14 @@ def main():
         peak, peak_src = load_peaks()
         value = world * B / (ms * 1e-3)
         e2e = world * B / (ms_e2e * 1e-3)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one conv launch from the committed `ncu --set full` capture
+        # (profiles/r01_ncu_traffic.json: which launch, its algorithmic FLOPs and duration are stated there)
+        conv_traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                conv_traffic = json.load(f)["conv_gemm"]
+        except Exception:
+            conv_traffic = None
         line = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -342,7 +350,7 @@ def main():
             "step_frac_of_peak": TFLOP_PER_IMAGE * B / (ms * 1e-3) / peak,
             "roofline": {"kernel": "vqb::conv_gemm_kernel (tcgen05 implicit-GEMM conv, fwd+dgrad launches of one step)",
                          "bound": "tensor", "achieved": prof["conv"]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                         "frac": prof["conv"]["tflops"] / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": prof["conv"]["tflops"] / peak, "traffic": conv_traffic, "peak_source": peak_src,
                          "launches_per_step": prof["conv"]["launches"], "ms_per_step": prof["conv"]["ms"],
                          "alg_flops_per_launch": prof["conv"]["flops_per_launch"],
                          "avg_launch_ms": prof["conv"]["ms_per_launch"]},
