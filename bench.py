@@ -169,7 +169,7 @@ def run_reference(args, rank, world):
                              "sample": f"{k} timed training steps at batch 1 (fwd+bwd+AdamW), torch CPU fp32"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def profile_conv_kernels(tr, batch_dev):
@@ -237,6 +237,15 @@ def profile_conv_kernels(tr, batch_dev):
     return out
 
 
+_JSON_OUT = None
+
+
+def emit_json(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -247,6 +256,14 @@ def main():
     ap.add_argument("--gan", action="store_true", help="configs[2]: + PatchDiscriminator hinge + GradNorm + LeCam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+
+    # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner from C at
+    # communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a
+    # private duplicate of the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -373,7 +390,7 @@ def main():
             line["cpu_baseline"] = {"value": b / dt, "unit": "images/s", "cores": threads, "kind": "port",
                                     "sample": f"{n} training steps at batch 1 of the same workload (oracle port of the "
                                               f"reference arithmetic, torch CPU fp32, {threads} threads)"}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
