@@ -219,3 +219,51 @@ def test_geom_upsample_fold_matches_nearest_upsample_conv():
     gd = plans.geom_up_dgrad(N, h, w, Co)
     gx = emulate_conv_gemm(gd, dy, fold(gd.tapmask, True), C)
     assert torch.allclose(gx, gref.permute(0, 2, 3, 1), atol=1e-4)
+
+
+def test_ksplit_fills_one_wave_of_148_ctas():
+    """Split-K is sized so that (tiles x splits) fills ONE wave of 148 persistent CTAs (measured faster than >= 2 waves,
+    DESIGN.md 3.2) for the weight-gradient shapes of the FLUX config at B=32."""
+    import ops
+
+    for (N, H, W, C, Co, tiles) in [(32, 32, 32, 512, 512, 36), (32, 256, 256, 128, 128, 6), (32, 64, 64, 512, 512, 36),
+                                    (32, 128, 128, 256, 256, 9), (32, 128, 128, 128, 256, 6)]:
+        ks = ops.choose_ksplit(plans.geom_s1(N, H, W, C, 3), Co)
+        assert tiles * ks <= 148 and tiles * ks >= 0.9 * 148, (N, H, W, C, Co, ks)
+
+
+def test_geom_fat3_matches_conv2d():
+    """Fat-pixel first-layer conv: 3 taps of one 64-element K run over the zero-framed 8-channel image (+ slack), weights
+    [Cout][kh][kw*8 + c] zero beyond column 24, == conv3x3 p1 over the 3 real channels; same for the data-gradient form."""
+    torch.manual_seed(11)
+    N, H, W, Co = 2, 5, 6, 4
+    x = torch.randn(N, 3, H, W)
+    wt = torch.randn(Co, 3, 3, 3)
+    framed = torch.zeros(N * (H + 2) * (W + 2) * 8 + 64)
+    fv = framed[:N * (H + 2) * (W + 2) * 8].view(N, H + 2, W + 2, 8)
+    fv[:, 1:H + 1, 1:W + 1, :3] = x.permute(0, 2, 3, 1)
+    g = plans.geom_fat3(N, H, W)
+    assert g.C == plans.FAT_K == 64 and len(g.taps) == 3
+    w9 = torch.zeros(Co, 9, 8)
+    w9[:, :, :3] = wt.reshape(Co, 3, 9).permute(0, 2, 1)  # [Cout][tap = kh*3+kw][c]
+    w64 = torch.zeros(Co, 3, 64)
+    w64[:, :, :24] = w9.view(Co, 3, 24)  # what ops._fat_weights builds from the ordinary [Cout][9][8] packing
+    out = emulate_conv_gemm(g, framed, w64, Co)
+    ref = F.conv2d(x, wt, padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(out, ref, atol=1e-4)
+
+
+def test_dx_colsum_side_channel_only_matches_the_very_tensor():
+    """ops._take_dx_colsum hands the bias gradient produced by the GroupNorm backward pass to the conv backward only for
+    the same, unmodified dx tensor; anything else falls back to vqb_colsum."""
+    import ops
+
+    dx, cs = torch.randn(2, 3, 3, 8), torch.randn(8)
+    ops._dx_colsum_slot[0] = (dx, dx._version, cs)
+    assert ops._take_dx_colsum(torch.randn(2, 3, 3, 8), 8) is None           # another tensor
+    assert ops._take_dx_colsum(dx, 16) is None                              # channel count mismatch
+    assert ops._take_dx_colsum(dx, 8) is cs and ops._dx_colsum_slot[0] is None  # hit consumes the slot
+    ops._dx_colsum_slot[0] = (dx, dx._version, cs)
+    dx.add_(1.0)                                                             # accumulated into in place
+    assert ops._take_dx_colsum(dx, 8) is None
+    ops._dx_colsum_slot[0] = None
