@@ -41,9 +41,18 @@ import torch
 import torch.distributed as dist
 
 CFG = dict(vae_ch=128, vae_ch_mult="1,2,4,4", vae_z_channels=16, vae_num_res_blocks=2, resolution=256)
-# algorithmic conv FLOPs per image of one training step (SURVEY.md §8a / BASELINE.md §3): fwd + dgrad + wgrad of the VAE,
-# 2 LPIPS VGG forwards + 1 dgrad
-TFLOP_PER_IMAGE = 2.780
+# BASELINE.json configs[1..4] -> bench modes. tflop = algorithmic conv FLOPs per image of one training step
+# (SURVEY.md §8a / BASELINE.md §3: fwd + dgrad + wgrad of the VAE, 2 LPIPS VGG forwards + 1 dgrad, + D passes).
+CONFIGS = {
+    "lpips": dict(idx=1, tflop=2.780, gan=False, vq=False, hr=False, res=256, batch=32,
+                  what="Encoder->clamp->Decoder->GradNorm->LPIPS(eval)+0.1*mean(z^2)"),
+    "gan": dict(idx=2, tflop=3.107, gan=True, vq=False, hr=False, res=256, batch=32,
+                what="Encoder->clamp->Decoder->GradNorm->LPIPS(eval)+0.1*mean(z^2)+PatchD hinge+LeCam (D step every step)"),
+    "vq": dict(idx=3, tflop=3.107, gan=True, vq=True, hr=False, res=256, batch=32,
+               what="Encoder->clamp->VQ(8192x16 argmin+commitment)->Decoder->GradNorm->LPIPS(eval)+PatchD hinge+LeCam"),
+    "hr512": dict(idx=4, tflop=9.98, gan=True, vq=False, hr=True, res=512, batch=8,
+                  what="Encoder@256^2->clamp->HR Decoder->512^2->GradNorm->LPIPS(eval)@512^2+PatchD hinge+LeCam@512^2"),
+}
 
 
 def load_peaks():
@@ -246,16 +255,175 @@ def emit_json(line):
     out.flush()
 
 
+def eager_b200_leg(cfg, B, world, rank, device, steps, warmup):
+    """The kernel-for-kernel bar (SURVEY.md §8d "Reference beside it (2)"): the reference's arithmetic executed by stock
+    PyTorch eager (cuDNN / ATen) on this same B200, with the reference's own precision mix — TF32 encoder / LPIPS / D
+    (vae_trainer.py:18-19), bf16-autocast decoder (:453,623), fp32 GroupNorm — fused AdamW, and the gradient all-reduce
+    the reference intends for N > 1. The reference tree is plain Python without packaging (`pip install /root/reference`
+    fails: no setup.py / pyproject.toml) and may not be copied, so its modules are represented by the oracle
+    restatement (oracle/*.py, pinned to the reference by tests/golden)."""
+    from oracle import lpips_oracle as LP
+    from oracle import step_oracle as SO
+    from oracle import vae_oracle as VO
+
+    vcfg = VO.VAEConfig(resolution=256, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16,
+                        decoder_also_perform_hr=cfg["hr"])
+    g = torch.Generator().manual_seed(42)
+
+    def init(shapes, skip=()):
+        sd = {}
+        for k, shp in shapes.items():
+            if any(t in k for t in skip):
+                continue
+            if len(shp) == 4:
+                fan = max(1, shp[1] * shp[2] * shp[3])
+                v = (torch.rand(shp, generator=g) / fan) if ("lin" in k) else torch.randn(shp, generator=g) * (2.0 / fan) ** 0.5
+            elif k.endswith("weight"):
+                v = torch.ones(shp)
+            else:
+                v = torch.zeros(shp)
+            sd[k] = v.to(device)
+        return sd
+
+    vsd = {k: v.requires_grad_(True) for k, v in init(VO.state_dict_shapes(vcfg)).items()}
+    lsd = init(LP.lpips_state_dict_shapes(), skip=("scaling",))
+    dsd = None
+    if cfg["gan"]:
+        dsd = {k: v.requires_grad_(True) for k, v in init(LP.patchd_state_dict_shapes(), skip=("scaling",)).items()}
+    named = list(vsd.items())
+    opt_g = torch.optim.AdamW([{"params": [v for k, v in named if "conv_in" not in k], "lr": 1e-5 / 128},
+                               {"params": [v for k, v in named if "conv_in" in k], "lr": 1e-4}],
+                              weight_decay=1e-3, betas=(0.9, 0.95), fused=True)
+    opt_d = torch.optim.AdamW(list(dsd.values()), lr=2e-4, weight_decay=1e-3, betas=(0.9, 0.95), fused=True) if dsd else None
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    R = cfg["res"]
+
+    def allreduce(params):
+        if world > 1:
+            gs = [p.grad for p in params if p.grad is not None]
+            flat = torch.cat([x.reshape(-1) for x in gs])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            torch._foreach_copy_(gs, list(flat.split([x.numel() for x in gs])))
+
+    def avg_fn(n):
+        if world > 1:
+            t = torch.tensor(n, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+            return t.item()
+        return n
+
+    def step(real_hr):
+        real_enc = torch.nn.functional.interpolate(real_hr, size=(256, 256), mode="area") if R != 256 else real_hr
+        if dsd is not None:  # discriminator pass (vae_trainer.py:629-659) on the detached reconstruction
+            with torch.no_grad():
+                z = VO.encoder_forward(vsd, real_enc, vcfg).clamp(-8.0, 8.0)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    rec = VO.decoder_forward(vsd, VO.reg(z), vcfg)
+            opt_d.zero_grad(set_to_none=True)
+            SO.discriminator_step(dsd, real_hr, rec.float(), "hinge", True, (0.0, 0.0))
+            allreduce(list(dsd.values()))
+            opt_d.step()
+            for v in dsd.values():
+                v.requires_grad_(False)
+        opt_g.zero_grad(set_to_none=True)
+        if R != 256:
+            o = _eager_generator_step_hr(SO, VO, LP, vsd, lsd, dsd, real_hr, real_enc, vcfg, avg_fn)
+        else:
+            o = SO.generator_step(vsd, lsd, dsd, real_hr, vcfg, do_clamp=True, do_ganloss=cfg["gan"], disc_type="hinge",
+                                  avg_fn=avg_fn, amp_decoder=True)
+        if dsd is not None:
+            for v in dsd.values():
+                v.requires_grad_(True)
+        allreduce([v for _, v in named])
+        opt_g.step()
+        return o["loss"]
+
+    tried = []
+    b = B
+    while b >= 1:
+        try:
+            gen = torch.Generator(device=device).manual_seed(1)
+            batches = [torch.rand(b, 3, R, R, device=device, generator=gen) * 2 - 1 for _ in range(2)]
+            for i in range(max(2, min(warmup, 3))):
+                step(batches[i % 2])
+            torch.cuda.synchronize()
+            k = max(2, min(steps, 5))
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(k):
+                loss = step(batches[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / k
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+            return {"value": world * b / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "per_gpu_batch": b,
+                    "steps": k, "last_loss": float(loss), "tried_batches": tried + [b],
+                    "impl": "reference arithmetic (oracle restatement of ae.py/utils.py/vae_trainer.py:530-708) in stock "
+                            "PyTorch eager on this GPU: cuDNN convs, TF32 encoder/LPIPS/D, bf16-autocast decoder, fp32 "
+                            "GroupNorm, fused AdamW, cudnn.benchmark=True",
+                    "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+        except torch.OutOfMemoryError:
+            tried.append(b)
+            if world > 1:
+                return {"unavailable": f"eager path out of memory at per-GPU batch {b} (no retry under NCCL)"}
+            opt_g.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
+            b //= 2
+    return {"unavailable": "eager path out of memory at every batch size", "tried_batches": tried}
+
+
+def _eager_generator_step_hr(SO, VO, LP, vsd, lsd, dsd, real_hr, real_enc, vcfg, avg_fn):
+    """configs[4]: encoder on the 256^2 area-resized image, HR decoder to 512^2, losses against the 512^2 image."""
+    from oracle import loss_oracle as LO
+
+    z = VO.encoder_forward(vsd, real_enc, vcfg).clamp(-8.0, 8.0)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        recon = VO.decoder_forward(vsd, VO.reg(z), vcfg)
+    percep = LP.lpips_forward(lsd, LO.gradnorm(recon, 1.0, avg_fn), real_hr).mean()
+    vae_loss, _ = LO.vae_loss_function(real_hr, LO.gradnorm(recon, 0.001, avg_fn), z, do_pool=True, do_recon=False,
+                                       recon_weight=0.0)
+    loss = percep + vae_loss
+    if dsd is not None:
+        loss = loss + LO.gan_gen_loss(LP.patchd_forward(dsd, LO.gradnorm(recon, 1.0, avg_fn)), "hinge")
+    loss.backward()
+    return {"loss": loss.detach()}
+
+
+def load_traffic_table():
+    """Measured DRAM traffic of the dominant conv shapes (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per
+    launch) next to their algorithmic bytes: profiles/r02_ncu_traffic.json when present, else the round-1 capture."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return name, json.load(f)
+        except Exception:
+            continue
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("VQB_BENCH_BATCH", "32")), help="per-GPU batch")
-    ap.add_argument("--gan", action="store_true", help="configs[2]: + PatchDiscriminator hinge + GradNorm + LeCam")
+    ap.add_argument("--config", type=str, default=os.environ.get("VQB_BENCH_CONFIG", "lpips"), choices=sorted(CONFIGS),
+                    help="lpips = BASELINE configs[1] (the metric's config), gan = [2], vq = [3], hr512 = [4]")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("VQB_BENCH_BATCH", "0")), help="per-GPU batch")
+    ap.add_argument("--gan", action="store_true", help="alias of --config gan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-B200 peer leg")
     args = ap.parse_args()
+    if args.gan and args.config == "lpips":
+        args.config = "gan"
+    cfg = CONFIGS[args.config]
 
     # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner from C at
     # communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a
@@ -282,11 +450,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(device))
     W = max(3, args.warmup)
     K = args.steps
-    B, R = args.batch, CFG["resolution"]
+    B, R = (args.batch or cfg["batch"]), cfg["res"]
 
-    tr = vt.Trainer(device, vae_resolution=R, vae_ch=CFG["vae_ch"], vae_ch_mult=CFG["vae_ch_mult"],
+    tr = vt.Trainer(device, vae_resolution=256, vae_ch=CFG["vae_ch"], vae_ch_mult=CFG["vae_ch_mult"],
                     vae_num_res_blocks=CFG["vae_num_res_blocks"], vae_z_channels=CFG["vae_z_channels"], do_clamp=True,
-                    do_ganloss=args.gan, disc_type="hinge", use_lecam=args.gan, max_steps=100000, lpips_eval=True)
+                    do_ganloss=cfg["gan"], disc_type="hinge", use_lecam=cfg["gan"], max_steps=100000, lpips_eval=True,
+                    use_vq=cfg["vq"], decoder_also_perform_hr=cfg["hr"])
     loader = vt.SyntheticLoader(B, R, seed=42 + rank, n_distinct=4)
     host_batches = loader.batches
     dev_batches = [b.to(device) for b in host_batches]
@@ -336,38 +505,53 @@ def main():
 
     # every rank runs the profiled extra step (it contains the NCCL collectives of a normal step); rank 0 reports it
     prof = profile_conv_kernels(tr, dev_batches[0])
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    # ---------------- the PyTorch-eager-on-B200 peer (same step, same batch, same GPUs), after freeing our own state
+    eager = None
+    if not args.no_eager:
+        del tr, out, o, dev_batches, loader
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        try:
+            eager = eager_b200_leg(cfg, B, world, rank, device, K, W)
+        except Exception as e:  # the peer must never take the product line down
+            eager = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
     if rank == 0:
         peak, peak_src = load_peaks()
         value = world * B / (ms * 1e-3)
         e2e = world * B / (ms_e2e * 1e-3)
-        # dram__bytes_read.sum + dram__bytes_write.sum of one conv launch from the committed `ncu --set full` capture
-        # (profiles/r01_ncu_traffic.json: which launch, its algorithmic FLOPs and duration are stated there)
+        tname, ttab = load_traffic_table()
         conv_traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-                conv_traffic = json.load(f)["conv_gemm"]
-        except Exception:
-            conv_traffic = None
+        if ttab is not None:
+            conv_traffic = ttab.get("conv_gemm_bytes_per_launch", ttab.get("conv_gemm"))
+        tflop = cfg["tflop"]
         line = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "FLUX-VAE ch=128 ch_mult=1,2,4,4 z=16 256x256: Encoder->clamp->Decoder->GradNorm->"
-                                   "LPIPS(eval)+0.1*mean(z^2)" + ("+PatchD hinge+LeCam" if args.gan else "") +
-                                   " fwd+bwd+grad all-reduce+AdamW (BASELINE.json configs[%d])" % (2 if args.gan else 1),
-                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
+            "config": {"workload": f"FLUX-VAE ch=128 ch_mult=1,2,4,4 z=16 {R}x{R}: {cfg['what']} fwd+bwd+grad all-reduce+"
+                                   f"AdamW+weight re-pack (BASELINE.json configs[{cfg['idx']}]); LPIPS in eval mode "
+                                   "(the reference trains with its Dropout(0.5) live; `Trainer(lpips_eval=False)` "
+                                   "reproduces that)",
+                       "name": args.config, "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "no explicit flush: per-step working set (activations ~0.9 GB/image) >> 126 MB L2",
-                       "tflop_per_image": TFLOP_PER_IMAGE},
+                       "tflop_per_image": tflop},
             "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 3 * R * R * 4,
                     "d2h_bytes_per_step": 4, "last_loss": last_loss},
             "gpu_launches": launches,
             "clocks": clocks,
-            "achieved_step_tflops_per_gpu": TFLOP_PER_IMAGE * B / (ms * 1e-3),
-            "step_frac_of_peak": TFLOP_PER_IMAGE * B / (ms * 1e-3) / peak,
+            "peak_mem_gib": peak_mem,
+            "achieved_step_tflops_per_gpu": tflop * B / (ms * 1e-3),
+            "step_frac_of_peak": tflop * B / (ms * 1e-3) / peak,
             "roofline": {"kernel": "vqb::conv_gemm_kernel (tcgen05 implicit-GEMM conv, fwd+dgrad launches of one step)",
                          "bound": "tensor", "achieved": prof["conv"]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                         "frac": prof["conv"]["tflops"] / peak, "traffic": conv_traffic, "peak_source": peak_src,
+                         "frac": prof["conv"]["tflops"] / peak, "traffic": conv_traffic, "traffic_source": tname,
+                         "traffic_per_shape": (ttab or {}).get("per_shape"), "peak_source": peak_src,
                          "launches_per_step": prof["conv"]["launches"], "ms_per_step": prof["conv"]["ms"],
                          "alg_flops_per_launch": prof["conv"]["flops_per_launch"],
                          "avg_launch_ms": prof["conv"]["ms_per_launch"]},
@@ -376,6 +560,10 @@ def main():
                                "frac": prof["wgrad"]["tflops"] / peak, "launches_per_step": prof["wgrad"]["launches"],
                                "ms_per_step": prof["wgrad"]["ms"]},
         }
+        if eager is not None:
+            line["eager_b200"] = eager
+            if "value" in eager:
+                line["vs_eager_b200"] = value / eager["value"]
         if world == 1 and not args.no_cpu_baseline:
             threads = cpu_threads()
             step, b = cpu_step_runner(batch=1, threads=threads)
@@ -388,8 +576,9 @@ def main():
                 step()
             dt = (time.perf_counter() - t0) / n
             line["cpu_baseline"] = {"value": b / dt, "unit": "images/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n} training steps at batch 1 of the same workload (oracle port of the "
-                                              f"reference arithmetic, torch CPU fp32, {threads} threads)"}
+                                    "sample": f"{n} training steps at batch 1 of the configs[1] workload (oracle port "
+                                              f"of the reference arithmetic, torch CPU fp32, {threads} threads); the "
+                                              "reference tree is unpackaged Python and cannot be installed/travel"}
         emit_json(line)
     if world > 1:
         dist.barrier()

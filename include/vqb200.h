@@ -205,6 +205,39 @@ int vqb_attn_bwd(const void* qkv, const void* out, const void* dout, const float
 int vqb_vq_argmin(const float* z, const float* e, long long* idx, float* zq, float* sqerr, int M, int K, int D,
                   void* stream);
 
+/*
+ * Optimizer step over ONE flat fp32 buffer holding every tensor of a model (each tensor padded to a multiple of 1024
+ * elements): torch.optim.AdamW semantics (decoupled weight decay, bias correction) with up to VQB_ADAMW_MAX_GROUPS
+ * hyper-parameter groups. chunk_group[i] (device, uint8) = group of 1024-element chunk i, 255 = skip (the owning tensor
+ * received no gradient). grads are multiplied by grad_scale first. groups_host is HOST memory (read during the call).
+ * Replaces: optimizer_G.step()/optimizer_D.step() = AdamW(lr groups, wd 1e-3, betas (0.9, 0.95)) at
+ * vae_trainer.py:455-475 with the cosine-with-warmup learning rate of :486-490 passed in as groups_host[].lr.
+ */
+#define VQB_ADAMW_MAX_GROUPS 4
+typedef struct VqbAdamwGroup {
+    float lr, beta1, beta2, eps, weight_decay;
+    int32_t step; /* 1-based step count of this group (bias correction) */
+} VqbAdamwGroup;
+int vqb_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* chunk_group,
+                   int64_t nchunks, int ngroups, const VqbAdamwGroup* groups_host, float grad_scale, void* stream);
+
+/*
+ * Re-pack every cached bf16 GEMM operand of the fp32 OIHW master weights in one launch (after an optimizer step).
+ * jobs_dev: DEVICE array of njobs descriptors; total_blocks = sum over jobs of ceil(R*nslots*Kpad / 2048).
+ *   out[r*ld_r + (slot/sg)*ld_g + (slot%sg)*Kpad + k] = bf16(transpose ? w[k][r][.] : w[r][k][.]); fold: tapmap entries are
+ *   bit masks of taps summed in fp32 (vqb_pack_weights_fold), else tap indices (vqb_pack_weights).
+ * Replaces: the per-step fp32->bf16 weight casts of torch.autocast (vae_trainer.py:453,623).
+ */
+typedef struct VqbPackJob {
+    const float* w;
+    void* out;
+    const int* tapmap;
+    int32_t Cout, Cin, T, nslots, transpose, Kpad, fold, sg, ld_g, ld_r;
+    int32_t first_block; /* prefix sum of ceil(total/2048) over the preceding jobs */
+    int32_t _pad;
+} VqbPackJob;
+int vqb_pack_weights_multi(const VqbPackJob* jobs_dev, int njobs, int total_blocks, void* stream);
+
 /* library / device info */
 const char* vqb_last_error(void);
 int vqb_version(void);

@@ -246,7 +246,140 @@ def step_case():
     save(name, **res)
 
 
+def _sub(tag, grads, res, keys, budget=60_000):
+    """Full gradient tensors are too large for a fixture at ch=128: store every s-th element of the flattened tensor
+    (s = smallest stride keeping <= budget elements; s == 1 keeps it whole) as `<tag>grad::<key>` and s as
+    `<tag>stride::<key>`; the exact norm of every tensor is in `<tag>grad_norms`."""
+    for k in keys:
+        g = grads[k].detach().flatten()
+        s = max(1, -(-g.numel() // budget))
+        res[f"{tag}grad::{k}"] = g[::s].clone()
+        res[f"{tag}stride::{k}"] = np.int64(s)
+
+
+FLUX_PICK = ("encoder.conv_in.weight", "encoder.down.0.block.0.conv1.weight", "encoder.down.0.downsample.conv.weight",
+             "encoder.down.1.block.0.nin_shortcut.weight", "encoder.down.3.block.1.conv2.weight",
+             "encoder.mid.block_1.norm1.weight", "encoder.conv_out.weight", "decoder.conv_in.weight",
+             "decoder.mid.block_2.conv1.weight", "decoder.up.1.upsample.conv.weight",
+             "decoder.up.0.block.0.nin_shortcut.weight", "decoder.up.0.block.2.conv2.weight",
+             "decoder.up.0.block.1.norm2.bias", "decoder.norm_out.weight", "decoder.conv_out.weight")
+
+
+def flux_step_case(name="step_flux", R=256):
+    """BASELINE.json configs[1]/[2] at B=1: ch=128, mult 1,2,4,4, z=16, 256x256 — the generator step without and with
+    the PatchDiscriminator term, then the discriminator step (hinge + LeCam), driven through the reference's own
+    modules exactly like step_case (vae_trainer.py:530-708)."""
+    import time
+
+    cfg = VO.VAEConfig(resolution=R, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16)
+    torch.manual_seed(0)
+    vae = ref_ae.VAE(resolution=R, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
+                     z_channels=16, use_attn=False, decoder_also_perform_hr=False, use_wavelet=False)
+    vsd = seeded.fill_state_dict(vae.state_dict(), name + "/vae")
+    vae.load_state_dict(vsd)
+    lp = ref_utils.LPIPS().eval()
+    lsd = seeded.fill_state_dict(lp.state_dict(), "lpips")
+    lp.load_state_dict(lsd)
+    disc = ref_utils.PatchDiscriminator()
+    dsd = seeded.fill_state_dict(disc.state_dict(), "patchd")
+    disc.load_state_dict(dsd)
+    real = seeded.tensor(name + "/real", (1, 3, R, R), 1.0, "uniform")
+    res = {}
+    for gan in (False, True):
+        t0 = time.time()
+        vae.zero_grad()
+        z = vae.encoder(real)
+        z = z.clamp(-8.0, 8.0)
+        z_s = vae.reg(z)
+        recon = vae.decoder(z_s)
+        percep = lp(ref_vt.gradnorm(recon), real).mean()
+        vl, _ = ref_vt.vae_loss_function(real, ref_vt.gradnorm(recon, weight=0.001), z)
+        if gan:
+            g = -disc(ref_vt.gradnorm(recon, weight=1.0)).mean()
+            loss = percep + g + vl
+        else:
+            loss = percep + vl
+        loss.backward()
+        print(f"  reference step gan={gan}: {time.time() - t0:.1f} s, loss {loss.item():.6f}", flush=True)
+        grads = {k: p.grad.detach().clone() for k, p in vae.named_parameters()}
+        osd = {k: v.clone().requires_grad_(True) for k, v in vsd.items()}
+        o = SO.generator_step(osd, lsd, dsd, real, cfg, do_clamp=True, do_ganloss=gan, disc_type="hinge")
+        close(o["loss"], loss, 1e-5, f"flux step loss gan={gan}")
+        for k in grads:
+            close(osd[k].grad, grads[k], 5e-4, f"flux step grad {k} gan={gan}")
+        keys = sorted(grads)
+        tag = "gan_" if gan else "nogan_"
+        res[tag + "loss"] = loss.detach()
+        res[tag + "percep"] = percep.detach()
+        res[tag + "grad_norms"] = np.array([grads[k].norm().item() for k in keys])
+        _sub(tag, grads, res, FLUX_PICK)
+        res["grad_keys"] = np.array(keys)
+        res["recon"] = recon.detach()
+        res["z"] = z.detach()
+    disc.zero_grad()
+    rp, fp = disc(real), disc(res["recon"])
+    dl, ar, af, acc = ref_vt.gan_disc_loss(rp, fp, "hinge")
+    lec = (rp - 0.05).pow(2).mean() + (fp - 0.1).pow(2).mean()
+    (dl.mean() + 0.1 * lec).backward()
+    dgr = {k: p.grad.detach().clone() for k, p in disc.named_parameters()}
+    osd = {k: v.clone().requires_grad_(torch.is_floating_point(v) and "scaling" not in k) for k, v in dsd.items()}
+    o = SO.discriminator_step(osd, real, res["recon"], "hinge", True, (0.1, 0.05))
+    close(o["d_loss"], dl.mean() + 0.1 * lec, 1e-5, "flux d step loss")
+    for k in dgr:
+        close(osd[k].grad, dgr[k], 5e-4, "flux d step grad " + k)
+    dkeys = sorted(dgr)
+    res["d_loss"] = (dl.mean() + 0.1 * lec).detach()
+    res["d_logits_real"] = rp.detach()
+    res["d_logits_fake"] = fp.detach()
+    res["d_grad_keys"] = np.array(dkeys)
+    res["d_grad_norms"] = np.array([dgr[k].norm().item() for k in dkeys])
+    _sub("d_", dgr, res, ("slice1.0.0.weight", "slice3.0.10.weight", "binary_classifier1.0.weight",
+                          "binary_classifier3.0.weight", "binary_classifier5.0.weight"))
+    res["recon"] = res["recon"].half()  # 3x256x256 image: fp16 storage keeps 3+ digits more than the test tolerance
+    save(name, **res)
+
+
+def flux_hr_case(name="vae_flux_hr", R=256):
+    """BASELINE.json configs[4] topology at B=1: ch=128 encoder at 256^2, decoder with the extra x2 "HR" level
+    (ae.py:381) -> 512^2 output."""
+    import time
+
+    cfg = VO.VAEConfig(resolution=R, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16,
+                       decoder_also_perform_hr=True)
+    ref = ref_ae.VAE(resolution=R, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
+                     z_channels=16, use_attn=False, decoder_also_perform_hr=True, use_wavelet=False)
+    sd = seeded.fill_state_dict(ref.state_dict(), name)
+    ref.load_state_dict(sd)
+    x = seeded.tensor(name + "/x", (1, 3, R, R), 1.0, "uniform")
+    t0 = time.time()
+    dec, z = ref(x)
+    loss = dec.pow(2).mean() + z.pow(2).mean()
+    loss.backward()
+    print(f"  reference HR fwd+bwd: {time.time() - t0:.1f} s, out {tuple(dec.shape)}", flush=True)
+    grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    odec, oz = VO.vae_forward(osd, x, cfg)
+    (odec.pow(2).mean() + oz.pow(2).mean()).backward()
+    close(oz, z, 1e-5, name + " z")
+    close(odec, dec, 1e-5, name + " dec")
+    for k in grads:
+        close(osd[k].grad, grads[k], 5e-4, name + " grad " + k)
+    keys = sorted(grads)
+    res = {"z": z.detach(), "dec": dec.detach().half(), "loss": loss.detach(), "grad_keys": np.array(keys),
+           "grad_norms": np.array([grads[k].norm().item() for k in keys], dtype=np.float64)}
+    _sub("", grads, res, ("encoder.conv_in.weight", "decoder.conv_out.weight", "decoder.up.4.block.0.conv1.weight",
+                          "decoder.up.4.upsample.conv.weight", "decoder.up.0.block.2.conv2.weight",
+                          "decoder.up.3.block.1.norm1.weight"))
+    save(name, **res)
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:  # e.g. `python oracle/make_golden.py flux_step flux_hr` (the ch=128 cases take minutes of CPU time)
+        for c in only:
+            {"flux_step": flux_step_case, "flux_hr": flux_hr_case}[c]()
+        dist.destroy_process_group()
+        sys.exit(0)
     vae_case("vae_small", VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=2, z_channels=4), 2, 32)
     vae_case("vae_attn", VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=4,
                                       use_attn=True), 2, 32, with_attn=True)
@@ -256,5 +389,7 @@ if __name__ == "__main__":
     patchd_case()
     losses_case()
     step_case()
+    flux_step_case()
+    flux_hr_case()
     dist.destroy_process_group()
     print("all golden fixtures written to", OUT)

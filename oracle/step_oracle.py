@@ -16,14 +16,18 @@ from . import vae_oracle as VO
 
 
 def generator_step(vae_sd, lpips_sd, disc_sd, real, cfg: VO.VAEConfig, do_clamp=True, clamp_th=8.0,
-                   do_ganloss=False, disc_type="hinge", recon_weight=0.0, avg_fn=None):
+                   do_ganloss=False, disc_type="hinge", recon_weight=0.0, avg_fn=None, amp_decoder=False):
     """Forward + backward of the generator (VAE) loss for one batch. `vae_sd` tensors must require grad.
     Returns dict(loss, percep, zloss, g_gan, recon, z) after calling backward (grads land in vae_sd tensors)."""
     z = VO.encoder_forward(vae_sd, real, cfg)                       # :538
     if do_clamp:
         z = z.clamp(-clamp_th, clamp_th)                            # :561-562
     z_s = VO.reg(z)                                                 # :563
-    recon = VO.decoder_forward(vae_sd, z_s, cfg)                    # :623-624
+    if amp_decoder:  # the reference's own precision mix on a GPU: decoder under bf16 autocast (:453,623), rest TF32 (:18-19)
+        with torch.autocast(device_type=z_s.device.type, dtype=torch.bfloat16):
+            recon = VO.decoder_forward(vae_sd, z_s, cfg)
+    else:
+        recon = VO.decoder_forward(vae_sd, z_s, cfg)                # :623-624
     rec_p = LO.gradnorm(recon, 1.0, avg_fn)                         # :662
     percep = LP.lpips_forward(lpips_sd, rec_p, real).mean()         # :676
     rec_m = LO.gradnorm(recon, 0.001, avg_fn)                       # :679

@@ -12,19 +12,24 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q, overlap, bucket_mb):
+def _worker(rank, world, port, q, use_store, ranges):
     sys.path.insert(0, os.path.join(ROOT, "vqgan-training_b200"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      VQB_OFFLINE="1", VQB_DDP_OVERLAP=overlap, VQB_DDP_BUCKET_MB=bucket_mb)
+                      VQB_OFFLINE="1")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import vae_trainer as vt
 
     torch.manual_seed(100 + rank)  # different init per rank: the wrapper must broadcast rank 0's weights
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     ddp = vt.FlatAllReduceDDP(net)
-    assert (ddp._buckets is not None) == (overlap == "1")
-    if overlap == "1" and float(bucket_mb) < 1e-3:
-        assert len(ddp._buckets) > 1  # the tiny bucket size must split the 4 parameters over several buckets
+    if use_store:  # the Trainer's configuration: gradients live in one flat buffer, reduced in place (in k async ranges)
+        import flat
+
+        store = flat.FlatParams(net.parameters())
+        ddp.attach_store(store, overlap_ranges=ranges)
+        assert (ddp._ranges is not None) == (ranges >= 2)
+        if ranges >= 2:
+            assert len(ddp._ranges) == ranges and sum(len(r["idx"]) for r in ddp._ranges) == 4
     w0 = [p.detach().clone() for p in net.parameters()]
     g = torch.Generator().manual_seed(7 + rank)
     x = torch.randn(4, 6, generator=g)
@@ -39,6 +44,8 @@ def _worker(rank, world, port, q, overlap, bucket_mb):
     loss.backward()
     ddp.allreduce_grads()
     avg = [p.grad.detach().clone() for p in net.parameters()]
+    if use_store:  # every gradient now lives in its slot of the flat buffer
+        assert all(p.grad.data_ptr() == store.grads.data_ptr() + 4 * o for p, o in zip(store.plist, store.offsets))
     s = vt.avg_scalar_over_nodes(float(rank + 1), "cpu")
     st = vt.avg_scalar_over_nodes(torch.tensor(float(rank + 1)), "cpu")
     # local norm of the gradient entering GradNorm (for the analytic check in the parent)
@@ -49,12 +56,12 @@ def _worker(rank, world, port, q, overlap, bucket_mb):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap,bucket_mb", [("1", "0.00005"), ("1", "64"), ("0", "64")])
-def test_flat_allreduce_gradnorm_world2(overlap, bucket_mb):
+@pytest.mark.parametrize("use_store,ranges", [(False, 0), (True, 0), (True, 2), (True, 4)])
+def test_flat_allreduce_gradnorm_world2(use_store, ranges):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 200) + {"0.00005": 0, "64": 1}[bucket_mb] + 2 * int(overlap)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap, bucket_mb)) for r in range(2)]
+    port = 29600 + (os.getpid() % 200) + ranges + int(use_store)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, use_store, ranges)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])

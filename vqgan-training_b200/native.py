@@ -42,6 +42,18 @@ class VqbWgradDesc(C.Structure):
                 ("views", VqbView * VQB_MAX_VIEWS), ("taps", VqbTap * VQB_MAX_TAPS)]
 
 
+class VqbPackJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("tapmap", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32),
+                ("T", C.c_int32), ("nslots", C.c_int32), ("transpose", C.c_int32), ("Kpad", C.c_int32),
+                ("fold", C.c_int32), ("sg", C.c_int32), ("ld_g", C.c_int32), ("ld_r", C.c_int32),
+                ("first_block", C.c_int32), ("_pad", C.c_int32)]
+
+
+class VqbAdamwGroup(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step", C.c_int32)]
+
+
 _lib = None
 
 
@@ -92,6 +104,8 @@ def load():
         "vqb_conv_stats_ok": (i32, [C.POINTER(VqbConvDesc)]),
         "vqb_pack_weights_fold": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
         "vqb_wgrad_reduce_fold": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "vqb_adamw_flat": (i32, [vp, vp, vp, vp, vp, i64, i32, C.POINTER(VqbAdamwGroup), f32, vp]),
+        "vqb_pack_weights_multi": (i32, [vp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name, None)

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from typing import Optional
 
 import torch
@@ -55,9 +56,123 @@ def pack_weights(weight: torch.Tensor, tapmap, transpose: bool, Kpad: int, fold:
     return out
 
 
+class _PackEntry:
+    """One cached bf16 GEMM operand of one fp32 OIHW parameter + the recipe to rebuild it in place."""
+
+    __slots__ = ("wref", "out", "tm", "spec", "ver", "__weakref__")
+
+    def __init__(self, weight, out, tm, spec):
+        self.wref = weakref.ref(weight)
+        self.out, self.tm, self.spec = out, tm, spec
+        self.ver = (weight._version, weight.data_ptr())
+
+    def job(self, first_block):
+        w = self.wref()
+        Cout, Cin, T, nslots, transpose, Kpad, fold, sg, ld_g, ld_r = self.spec
+        return native.VqbPackJob(w=w.data_ptr(), out=self.out.data_ptr(), tapmap=self.tm.data_ptr(), Cout=Cout, Cin=Cin,
+                                 T=T, nslots=nslots, transpose=transpose, Kpad=Kpad, fold=fold, sg=sg, ld_g=ld_g,
+                                 ld_r=ld_r, first_block=first_block, _pad=0)
+
+    def blocks(self):
+        Cout, Cin, T, nslots, transpose, Kpad = self.spec[:6]
+        return -(-((Cin if transpose else Cout) * nslots * Kpad) // 2048)
+
+
+# every live pack entry, by the data_ptr of the fp32 master weight it was packed from (weak: caches own the entries)
+_pack_registry = {}
+_pack_tables = {}
+
+
+def _new_pack_entry(weight, tapmap, transpose, Kpad, fold, fat=False) -> _PackEntry:
+    Cout, Cin, KH, KW = weight.shape
+    R = Cin if transpose else Cout
+    nslots = len(tapmap)
+    if fat:  # [R][9 slots][8] -> [R][3][64]: columns kw*8 + c of each kh row, zero beyond 24 (plans.geom_fat3)
+        assert nslots == 9 and Kpad == 8
+        out = torch.zeros(R, 3, plans.FAT_K, device=weight.device, dtype=torch.bfloat16)
+        spec = (Cout, Cin, KH * KW, nslots, 1 if transpose else 0, Kpad, 0, 3, plans.FAT_K, 3 * plans.FAT_K)
+    else:
+        out = torch.empty(R, nslots, Kpad, device=weight.device, dtype=torch.bfloat16)
+        spec = (Cout, Cin, KH * KW, nslots, 1 if transpose else 0, Kpad, 1 if fold else 0, nslots, 0, nslots * Kpad)
+    if weight.dtype != torch.float32 or not weight.is_contiguous():
+        raise RuntimeError("vqgan-training_b200: conv master weights must be contiguous fp32 OIHW tensors")
+    ent = _PackEntry(weight, out, tapmap_tensor(tapmap, weight.device), spec)
+    _pack_registry.setdefault(weight.data_ptr(), weakref.WeakSet()).add(ent)
+    return ent
+
+
+def _run_pack(entries):
+    """Re-packs `entries` (in place) with ONE vqb_pack_weights_multi launch; the device job table is cached per entry set."""
+    if not entries:
+        return
+    key = tuple(id(e) for e in entries)
+    tab = _pack_tables.get(key)
+    if tab is None or any(r() is None for r in tab[3]):
+        jobs, nb = [], 0
+        for e in entries:
+            jobs.append(e.job(nb))
+            nb += e.blocks()
+        arr = (native.VqbPackJob * len(jobs))(*jobs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        dev = host.to(entries[0].out.device)
+        if len(_pack_tables) > 64:
+            _pack_tables.clear()
+        tab = (dev, len(jobs), nb, [weakref.ref(e) for e in entries])
+        _pack_tables[key] = tab
+    check(_L().vqb_pack_weights_multi(tab[0].data_ptr(), tab[1], tab[2], stream_ptr()), "pack_weights_multi")
+    for e in entries:
+        w = e.wref()
+        e.ver = (w._version, w.data_ptr())
+
+
+def weights_updated(params=None):
+    """Call after master weights changed through a path that does not bump `Tensor._version` (fused / foreach optimizers,
+    `.data` writes such as a DDP broadcast): re-packs every cached bf16 operand of `params` (all parameters if None) in
+    one launch. A global optimizer post-step hook (registered below) calls this for every torch.optim optimizer."""
+    if params is None:
+        ptrs = list(_pack_registry.keys())
+    else:
+        ptrs = [p.data_ptr() for p in params]
+    entries = []
+    for dp in ptrs:
+        ws = _pack_registry.get(dp)
+        if not ws:
+            continue
+        for e in list(ws):
+            w = e.wref()
+            if w is None or w.data_ptr() != dp:
+                ws.discard(e)
+                continue
+            entries.append(e)
+        if not ws:
+            _pack_registry.pop(dp, None)
+    if entries:
+        entries.sort(key=id)
+        with torch.no_grad():
+            _run_pack(entries)
+
+
+def _optimizer_post_step(optimizer, args, kwargs):
+    try:
+        params = [p for g in optimizer.param_groups for p in g["params"] if p.is_cuda]
+    except Exception:  # pragma: no cover
+        params = None
+    if params is None or params:
+        weights_updated(params)
+
+
+try:  # fused AdamW (and any .data-style update) does not bump _version: never trust the version alone (ADVICE r1, high)
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+
+    _reg_hook(_optimizer_post_step)
+except Exception:  # pragma: no cover
+    pass
+
+
 class PackedCache:
-    """Per-conv-layer caches: bf16 packed copies of the fp32 OIHW parameter (refreshed when the parameter changes) and
-    the shape-dependent geometry objects / C descriptors (built once per input shape)."""
+    """Per-conv-layer caches: bf16 packed copies of the fp32 OIHW parameter and the shape-dependent geometry objects /
+    C descriptors (built once per input shape). A packed copy is valid while (parameter version, data_ptr) are unchanged;
+    updates that bypass the version counter are announced through `weights_updated` (global optimizer post-step hook)."""
 
     def __init__(self):
         self._store = {}
@@ -70,13 +185,45 @@ class PackedCache:
             self._geoms[key] = g
         return g
 
-    def get(self, weight: torch.Tensor, key, tapmap, transpose, Kpad, fold=False):
-        ver = (weight._version, weight.data_ptr())
+    def get(self, weight: torch.Tensor, key, tapmap, transpose, Kpad, fold=False, fat=False):
         ent = self._store.get(key)
-        if ent is None or ent[0] != ver:
-            ent = (ver, pack_weights(weight, tapmap, transpose, Kpad, fold))
+        if ent is None or ent.wref() is None or ent.ver[1] != weight.data_ptr() or \
+                tuple(ent.out.shape[:1]) != ((weight.shape[1] if transpose else weight.shape[0]),):
+            ent = _new_pack_entry(weight, tapmap, transpose, Kpad, fold, fat)
             self._store[key] = ent
-        return ent[1]
+            with torch.no_grad():
+                _run_pack([ent])
+        elif ent.ver[0] != weight._version:
+            with torch.no_grad():
+                _run_pack([ent])
+        return ent.out
+
+
+# Gradient slots: when a parameter lives in a flat.FlatParams store, the kernels that produce its gradient write straight
+# into the matching slot of the store's flat gradient buffer and return that view; autograd adopts it as `param.grad`
+# (no per-tensor gradient allocation, no copy-in before the all-reduce / fused optimizer).
+_grad_slots = {}
+
+
+def register_grad_slot(param, store, index):
+    _grad_slots[param.data_ptr()] = (weakref.ref(store), index)
+
+
+def grad_out(param: torch.Tensor) -> torch.Tensor:
+    """fp32 destination for the gradient of `param`: its flat-store slot (first contribution of this accumulation
+    window) or a fresh tensor."""
+    ent = _grad_slots.get(param.data_ptr())
+    if ent is not None:
+        store = ent[0]()
+        if store is None:
+            _grad_slots.pop(param.data_ptr(), None)
+        else:
+            q = store.plist[ent[1]]
+            if q.data_ptr() == param.data_ptr() and q.shape == param.shape:
+                s = store.take_slot(ent[1])
+                if s is not None:
+                    return s
+    return torch.empty(param.shape, device=param.device, dtype=torch.float32)
 
 
 def _wgrad_block_n(cols: int) -> int:
@@ -151,7 +298,7 @@ def conv_stats_supported(g: plans.ConvGeom, Cout: int, out_strides) -> bool:
 
 
 def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape, Cout_pad: int,
-              dy_view=None) -> torch.Tensor:
+              dy_view=None, out=None) -> torch.Tensor:
     """-> OIHW fp32 gradient for a conv whose forward geometry is g (weight_shape = (Cout, K per tap, taps_h, taps_w))."""
     Cout, Cin, KH, KW = weight_shape
     wk = ("wgrad", Cout_pad, dy_view is not None)
@@ -164,7 +311,8 @@ def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape
     ksplit, d, cols = ent
     partial = torch.empty(ksplit, Cout_pad, cols, device=x.device, dtype=torch.float32)
     check(_L().vqb_wgrad_gemm(d, ptr(dy), ptr(x), ptr(partial), stream_ptr()), "wgrad_gemm")
-    grad = torch.empty(Cout, Cin, KH, KW, device=x.device, dtype=torch.float32)
+    grad = out if out is not None else torch.empty(Cout, Cin, KH, KW, device=x.device, dtype=torch.float32)
+    assert grad.shape == (Cout, Cin, KH, KW) and grad.is_contiguous()
     tm = tapmap_tensor(g.tapmap if len(g.tapmap) == len(g.taps) else list(range(len(g.taps))), x.device)
     check(_L().vqb_wgrad_reduce(ptr(partial), ptr(grad), ksplit, Cout, Cout_pad, Cin, KH * KW, len(g.taps),
                                 cols // len(g.taps), ptr(tm), 0, stream_ptr()), "wgrad_reduce")
@@ -190,8 +338,9 @@ def _take_dx_colsum(dy: torch.Tensor, C: int):
     return None
 
 
-def colsum(x2d_rows: int, x: torch.Tensor, C: int) -> torch.Tensor:
-    out = torch.empty(C, device=x.device, dtype=torch.float32)
+def colsum(x2d_rows: int, x: torch.Tensor, C: int, out=None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(C, device=x.device, dtype=torch.float32)
     check(_L().vqb_colsum(ptr(x), ptr(out), x2d_rows, C, stream_ptr()), "colsum")
     return out
 
@@ -243,18 +392,8 @@ def alloc_framed(N, H, W, C, device) -> torch.Tensor:
 
 
 def _fat_weights(cache: "PackedCache", weight, key, tapmap, transpose, Kpad):
-    """[R][9 slots][8] packing -> [R][3][64]: columns kw*8 + c of each kh row, zero beyond 24 (plans.geom_fat3)."""
-    ver = (weight._version, weight.data_ptr())
-    k64 = tuple(key) + ("k64",)
-    ent = cache._store.get(k64)
-    if ent is None or ent[0] != ver:
-        wp = cache.get(weight, key, tapmap, transpose, Kpad)
-        R = wp.shape[0]
-        w64 = torch.zeros(R, 3, plans.FAT_K, device=wp.device, dtype=wp.dtype)
-        w64[:, :, :24] = wp.view(R, 3, 24)
-        ent = (ver, w64)
-        cache._store[k64] = ent
-    return ent[1]
+    """[R][9 slots][8] packing laid out as [R][3][64]: columns kw*8 + c of each kh row, zero beyond 24 (plans.geom_fat3)."""
+    return cache.get(weight, tuple(key) + ("k64",), tapmap, transpose, Kpad, fat=True)
 
 
 _fat_state = {"ok": None}
@@ -443,9 +582,9 @@ class ConvFn(torch.autograd.Function):
                 gw = g3[:, :24, :, 0].reshape(Cout, 3, 8, 3)[:, :, :Cin, :].permute(0, 2, 3, 1).contiguous()
             elif dy_framed:
                 gw = run_wgrad(g, x, dy, weight.shape, Cop,
-                               dy_view=plans.framed_interior_view(N, g.Ho, g.Wo, Cop))
+                               dy_view=plans.framed_interior_view(N, g.Ho, g.Wo, Cop), out=grad_out(weight))
             else:
-                gw = run_wgrad(g, x, dy, weight.shape, Cop)
+                gw = run_wgrad(g, x, dy, weight.shape, Cop, out=grad_out(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             rows = N * (g.Ho + 2) * (g.Wo + 2) if dy_framed else N * g.Ho * g.Wo  # the zero frame adds nothing
             gb = None if dy_framed else _take_dx_colsum(dy, Cop)
@@ -535,7 +674,7 @@ class UpConvFn(torch.autograd.Function):
                         descs[dk] = d
                     check(_L().vqb_wgrad_gemm(d, ptr(dy), ptr(x), ptr(partial), stream_ptr()), "wgrad_gemm(up)")
                     masks += g.tapmask
-            gw = torch.empty(Cout, Cin, 3, 3, device=x.device, dtype=torch.float32)
+            gw = grad_out(weight)
             tm = tapmap_tensor(masks, x.device)
             check(_L().vqb_wgrad_reduce_fold(ptr(partial), ptr(gw), ksplit, Cout, Cop, Cin, 9, 16, C64, ptr(tm),
                                              stream_ptr()), "wgrad_reduce_fold")
@@ -595,8 +734,7 @@ class GroupNormSiLUFn(torch.autograd.Function):
         gy = gy.contiguous()
         add = gskip.contiguous() if gskip is not None else None
         dx = torch.empty_like(x)
-        dg = torch.empty(C, device=x.device, dtype=torch.float32)
-        db = torch.empty(C, device=x.device, dtype=torch.float32)
+        dg, db = grad_out(gamma), grad_out(beta)
         ws = torch.empty(N * C * 2 + N * ctx.groups * 2, device=x.device, dtype=torch.float32)
         ga, be = gamma.detach().float(), beta.detach().float()
         cs = torch.empty(C, device=x.device, dtype=torch.float32) if _GN_COLSUM else None

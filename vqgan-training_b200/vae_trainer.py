@@ -200,15 +200,13 @@ class FlatAllReduceDDP(nn.Module):
     constructor broadcast from rank 0) whose gradient averaging is explicit — it therefore also covers the
     `vae.module.encoder(...)` calling style that bypasses DDP.forward in the reference.
 
-    VQB_DDP_OVERLAP=1 (opt-in): parameters are grouped, in reverse registration order (~ the order backward produces
-    their gradients), into flat fp32 buckets of VQB_DDP_BUCKET_MB (64) MiB. A post-accumulate-grad hook copies each
-    finished gradient into its bucket slot (the slot then IS `param.grad`) and, when a bucket is complete, launches its
-    NCCL all-reduce(AVG) asynchronously, so the transfer runs under the rest of backward; `allreduce_grads()` after
-    backward only waits. Requires one backward per `allreduce_grads()` call (what the training step does).
-    Default (VQB_DDP_OVERLAP=0): one flat all-reduce issued by `allreduce_grads()` after backward. Measured at N=2
-    (B=32/GPU): 100.4 ms/step flat vs 100.9 ms bucketed-overlapped vs 98.6 ms on one GPU — the persistent 148-CTA conv
-    kernels own every SM's shared memory, so an NCCL kernel launched mid-backward cannot co-reside and the overlap buys
-    nothing; the flat form stays the default."""
+    With a flat gradient store attached (`attach_store`, flat.FlatParams — what Trainer does) the weight-gradient kernels
+    have already written into one contiguous fp32 buffer, so `allreduce_grads()` is ONE in-place NCCL all-reduce(AVG)
+    with no copy-in / copy-out. VQB_DDP_OVERLAP=k (k >= 2, opt-in) splits that buffer into k contiguous ranges (in
+    parameter registration order: the decoder's range completes first in backward) and launches each range's
+    all-reduce asynchronously from a post-accumulate-grad hook as soon as its last gradient has landed;
+    `allreduce_grads()` then only waits. Without a store (plain modules, tests) gradients are staged through a
+    temporary flat buffer."""
 
     def __init__(self, module: nn.Module, device_ids=None):
         super().__init__()
@@ -216,71 +214,78 @@ class FlatAllReduceDDP(nn.Module):
         if _dist_on():
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, 0)
+            if any(p.is_cuda for p in module.parameters()):
+                import ops
+
+                ops.weights_updated(list(module.parameters()))  # .data writes do not bump Tensor._version
         self._flat = None
-        self._buckets = None
-        self._where = {}
-        if _dist_on() and os.environ.get("VQB_DDP_OVERLAP", "0") == "1":
-            self._build_buckets(float(os.environ.get("VQB_DDP_BUCKET_MB", "64")))
+        self._store = None
+        self._ranges = None
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
 
-    def _build_buckets(self, bucket_mb: float):
-        params = [p for p in self.module.parameters() if p.requires_grad]
-        cap = max(1, int(bucket_mb * (1 << 20) / 4))
-        groups, cur, n = [], [], 0
-        for p in reversed(params):
-            cur.append(p)
-            n += p.numel()
-            if n >= cap:
-                groups.append(cur)
-                cur, n = [], 0
-        if cur:
-            groups.append(cur)
-        self._buckets = []
-        for grp in groups:
-            flat = torch.zeros(sum(p.numel() for p in grp), device=grp[0].device, dtype=torch.float32)
-            views, off = [], 0
-            for p in grp:
-                views.append(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-            bk = {"params": grp, "flat": flat, "views": views, "ready": 0, "work": None}
-            for i, p in enumerate(grp):
-                self._where[p] = (bk, i)
+    def attach_store(self, store, overlap_ranges=None):
+        """Gradients of this module live in `store.grads` (flat.FlatParams): all-reduce that buffer in place."""
+        self._store = store
+        k = int(os.environ.get("VQB_DDP_OVERLAP", "0")) if overlap_ranges is None else overlap_ranges
+        if k >= 2 and _dist_on():
+            self._build_ranges(k)
+
+    def _build_ranges(self, k: int):
+        st = self._store
+        target = st.total / k
+        self._ranges, self._range_of = [], {}
+        lo = 0
+        for r in range(k):
+            hi = lo
+            while hi < len(st.plist) and (r == k - 1 or st.offsets[hi] < target * (r + 1)):
+                hi += 1
+            if hi == lo:
+                continue
+            a = st.offsets[lo]
+            b = st.offsets[hi] if hi < len(st.plist) else st.total
+            self._ranges.append({"idx": range(lo, hi), "a": a, "b": b, "ready": 0, "work": None})
+            lo = hi
+        for ri, rg in enumerate(self._ranges):
+            for i in rg["idx"]:
+                p = st.plist[i]
+                self._range_of[p] = ri
                 p.register_post_accumulate_grad_hook(self._grad_ready)
-            self._buckets.append(bk)
+
+    @torch.no_grad()
+    def _launch_range(self, rg):
+        st = self._store
+        st.collect(rg["idx"])
+        rg["work"] = dist.all_reduce(st.grads[rg["a"]:rg["b"]], op=dist.ReduceOp.AVG, async_op=True)
 
     @torch.no_grad()
     def _grad_ready(self, p):
-        bk, i = self._where[p]
-        if bk["work"] is not None:
-            raise RuntimeError("FlatAllReduceDDP: a second backward reached a bucket that is already being reduced; "
-                               "call allreduce_grads() after every backward or set VQB_DDP_OVERLAP=0")
-        v = bk["views"][i]
-        if p.grad is not v:
-            v.copy_(p.grad)
-            p.grad = v  # the optimizer reads the averaged gradient straight from the bucket
-        bk["ready"] += 1
-        if bk["ready"] == len(bk["params"]):
-            bk["work"] = dist.all_reduce(bk["flat"], op=dist.ReduceOp.AVG, async_op=True)
+        rg = self._ranges[self._range_of[p]]
+        if rg["work"] is not None:
+            raise RuntimeError("FlatAllReduceDDP: a second backward reached a range that is already being reduced; "
+                               "call allreduce_grads() after every backward or unset VQB_DDP_OVERLAP")
+        rg["ready"] += 1
+        if rg["ready"] == len(rg["idx"]):
+            self._launch_range(rg)
 
     @torch.no_grad()
     def allreduce_grads(self):
         if not _dist_on():
             return
-        if self._buckets is not None:
-            rest = [p for p in self.module.parameters()
-                    if p.requires_grad and p.grad is not None and p not in self._where]
-            for bk in self._buckets:
-                if bk["ready"] == 0:
-                    continue  # no gradient reached this bucket in this step (same on every rank)
-                if bk["work"] is None:  # some parameters of the bucket were unused: reduce what is there
-                    bk["work"] = dist.all_reduce(bk["flat"], op=dist.ReduceOp.AVG, async_op=True)
-                bk["work"].wait()
-                bk["work"], bk["ready"] = None, 0
-            params = rest
-        else:
-            params = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
+        if self._store is not None:
+            if self._ranges is None:
+                self._store.collect()
+                dist.all_reduce(self._store.grads, op=dist.ReduceOp.AVG)
+                return
+            for rg in self._ranges:
+                if rg["work"] is None:  # some parameter of the range got no gradient this step (same on every rank)
+                    self._launch_range(rg)
+            for rg in self._ranges:
+                rg["work"].wait()
+                rg["work"], rg["ready"] = None, 0
+            return
+        params = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
         if not params:
             return
         n = sum(p.numel() for p in params)
@@ -346,13 +351,22 @@ class Trainer:
         prepare_filter(device)
         self.discriminator = FlatAllReduceDDP(discriminator)
 
-        self.optimizer_G = optim.AdamW(
-            [{"params": [p for n, p in self.vae.named_parameters() if "conv_in" not in n],
-              "lr": learning_rate_vae / vae_ch},
-             {"params": [p for n, p in self.vae.named_parameters() if "conv_in" in n], "lr": 1e-4}],
-            weight_decay=1e-3, betas=(0.9, 0.95), fused=True)
-        self.optimizer_D = optim.AdamW(self.discriminator.parameters(), lr=learning_rate_disc, weight_decay=1e-3,
-                                       betas=(0.9, 0.95), fused=True)
+        # vae_trainer.py:455-475: two AdamW groups for the VAE (conv_in at 1e-4, the rest at lr/ch), one for D — as ONE
+        # fused kernel each over flat parameter/gradient/moment buffers (flat.FlatAdamW). The [extension] VQ codebook
+        # gets its own group at the un-divided VAE learning rate (it would never move at lr/ch).
+        from flat import FlatAdamW
+
+        named = list(self.vae.named_parameters())
+        groups = [{"params": [p for n, p in named if "conv_in" not in n and "reg.embedding" not in n],
+                   "lr": learning_rate_vae / vae_ch},
+                  {"params": [p for n, p in named if "conv_in" in n], "lr": 1e-4}]
+        if use_vq:
+            groups.append({"params": [p for n, p in named if "reg.embedding" in n], "lr": learning_rate_vae})
+        self.optimizer_G = FlatAdamW(groups, weight_decay=1e-3, betas=(0.9, 0.95))
+        self.optimizer_D = FlatAdamW([{"params": list(self.discriminator.parameters()), "lr": learning_rate_disc}],
+                                     weight_decay=1e-3, betas=(0.9, 0.95))
+        self.vae.attach_store(self.optimizer_G.store)
+        self.discriminator.attach_store(self.optimizer_D.store)
         self.lpips = LPIPS().to(device)
         if lpips_eval:
             self.lpips.eval()
