@@ -160,10 +160,19 @@ int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, co
                     const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
                     float* dx_colsum, void* stream);
 
-/* bring-up experiment only (csrc/dbg_shift.cu): one M=128,N=64,K=64 MMA whose A descriptor starts shift_rows rows into a
- * TMA-written 128B-swizzled tile with 8-row groups sbo_bytes apart */
+#ifdef VQB_DEBUG
+/* bring-up experiment only (csrc/dbg_shift.cu, libvqb200_dbg.so): one M=128,N=64,K=64 MMA whose A descriptor starts
+ * shift_rows rows into a TMA-written 128B-swizzled tile with 8-row groups sbo_bytes apart */
 int vqb_dbg_shift_mma(const void* X, int R, const void* B, float* out, int shift_rows, int sbo_bytes, int base_offset,
                       void* stream);
+#endif
+
+/*
+ * Wavelet front-end of the encoder (--use_wavelet; utils.py:229-247): F.pad(x, 2) + grouped 6x6 stride-2 conv with the
+ * four fixed analysis filters filt[4][6][6] (device, fp32), fused with the NCHW fp32 -> NHWC bf16 conversion:
+ * y[n][ho][wo][c*4 + band], Cpad channels (pad = 0). Input-side op, no gradient (the input is data).
+ */
+int vqb_wavelet_fwd(const float* x, void* y, const float* filt, int N, int C, int H, int W, int Cpad, void* stream);
 
 /* nearest-neighbour x2 up-sampling (ae.py:165) and its backward (2x2 sum), bf16 NHWC */
 int vqb_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
@@ -187,6 +196,18 @@ int vqb_maxpool2_bwd(const void* x, const void* dy, const void* add, void* dx, i
 int vqb_lpips_tail_fwd(const void* f0, const void* f1, const float* w, float* out, int N, int HW, int C, void* stream);
 int vqb_lpips_tail_bwd(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW, int C,
                        void* stream);
+/*
+ * Train-mode variants: the nn.Dropout(0.5) in front of every lin layer (utils.py:79-89) is live in the reference's
+ * training loop (LPIPS is never put in eval mode, vae_trainer.py:477). Element (n, p, c) of the squared-difference tensor
+ * is kept (and scaled by 2) iff bit ((n*HW + p)*C + c) of a counter-based hash stream of `seed` is set; forward and
+ * backward regenerate the same bits, and vqb_lpips_dropout_mask writes them out ([N][HW][C] bytes, 1 = keep) so that a
+ * test can feed the identical mask to the reference arithmetic.
+ */
+int vqb_lpips_tail_fwd_dropout(const void* f0, const void* f1, const float* w, float* out, int N, int HW, int C,
+                               uint64_t seed, void* stream);
+int vqb_lpips_tail_bwd_dropout(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW,
+                               int C, uint64_t seed, void* stream);
+int vqb_lpips_dropout_mask(uint64_t seed, int N, int HW, int C, uint8_t* mask, void* stream);
 
 /*
  * Multi-head self-attention core of AttnBlock (ae.py:74-93): qkv [N][T][3C] bf16 (q | k | v channel blocks, heads of 64
@@ -243,7 +264,7 @@ const char* vqb_last_error(void);
 int vqb_version(void);
 int vqb_device_ok(void); /* 1 if the current device is sm_100 and the TMA driver entry point resolved */
 int vqb_kernel_launch_count(void); /* number of kernels this library launched in this process */
-int vqb_set_debug_mode(int mode);   /* perf-experiment switches (tools/perf_experiments.py); 0 = production */
+int vqb_set_debug_mode(int mode);   /* perf-experiment switches: only the -DVQB_DEBUG build accepts mode != 0 */
 
 #ifdef __cplusplus
 }

@@ -117,3 +117,30 @@ def cosine_lr_factor(step, warmup, total):  # transformers.get_cosine_schedule_w
         return step / max(1, warmup)
     progress = (step - warmup) / max(1, total - warmup)
     return max(0.0, 0.5 * (1.0 + math.cos(math.pi * 0.5 * 2.0 * progress)))
+
+
+def latent_augment(z, z_s, real_hr, flip_invariance, crop_invariance, downscale_factor=16, hr=False, rnd=None):
+    """vae_trainer.py:566-621 restated line by line (python `random` draw order included); `rnd` = the random module or
+    a random.Random instance."""
+    import random as _random
+
+    rnd = rnd or _random
+    if rnd.random() < 0.5 and flip_invariance:
+        z_s = torch.flip(z_s, [-1])
+        z_s[:, -4:-2] = -z_s[:, -4:-2]
+        real_hr = torch.flip(real_hr, [-1])
+    if rnd.random() < 0.5 and flip_invariance:
+        z_s = torch.flip(z_s, [-2])
+        z_s[:, -2:] = -z_s[:, -2:]
+        real_hr = torch.flip(real_hr, [-2])
+    if rnd.random() < 0.5 and crop_invariance:
+        z_h, z_w = z.shape[-2:]
+        new_z_h = rnd.randint(12, z_h - 1)
+        new_z_w = rnd.randint(12, z_w - 1)
+        offset_z_h = rnd.randint(0, z_h - new_z_h - 1)
+        offset_z_w = rnd.randint(0, z_w - new_z_w - 1)
+        m = downscale_factor * 2 if hr else downscale_factor
+        new_h, new_w, offset_h, offset_w = new_z_h * m, new_z_w * m, offset_z_h * m, offset_z_w * m
+        real_hr = real_hr[:, :, offset_h:offset_h + new_h, offset_w:offset_w + new_w]
+        z_s = z_s[:, :, offset_z_h:offset_z_h + new_z_h, offset_z_w:offset_z_w + new_z_w]
+    return z_s, real_hr

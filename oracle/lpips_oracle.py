@@ -15,8 +15,8 @@ SHIFT = torch.tensor([-0.030, -0.088, -0.188])  # utils.py:63-68
 SCALE = torch.tensor([0.458, 0.448, 0.450])
 
 
-def scaling_layer(x):  # utils.py:70-71
-    return (x - SHIFT.to(x)[None, :, None, None]) / SCALE.to(x)[None, :, None, None]
+def scaling_layer(x):  # utils.py:63-71: shift/scale are fp32 buffers -> a bf16 input (autocast decoder output) promotes to fp32
+    return (x - SHIFT.to(x.device)[None, :, None, None]) / SCALE.to(x.device)[None, :, None, None]
 
 
 def vgg_features(sd, x, key_fmt):
@@ -48,13 +48,17 @@ def normalize_tensor(x, eps=1e-10):  # utils.py:134-136 (eps added AFTER the sqr
     return x / (torch.sqrt(torch.sum(x ** 2, dim=1, keepdim=True)) + eps)
 
 
-def lpips_forward(sd, inp, tgt):
-    """utils.py:39-57 in eval mode (dropout off): -> [B,1,1,1]."""
+def lpips_forward(sd, inp, tgt, keep_masks=None):
+    """utils.py:39-57 -> [B,1,1,1]. keep_masks=None: eval mode (dropout off). keep_masks = five [B,C,H,W] 0/1 tensors:
+    the train-mode nn.Dropout(0.5) of NetLinLayer (utils.py:79-89) with that explicit keep mask, i.e. exactly
+    F.dropout's arithmetic `x * mask / (1 - p)` in front of the 1x1 lin conv."""
     f0 = vgg_features(sd, scaling_layer(inp), lpips_key)
     f1 = vgg_features(sd, scaling_layer(tgt), lpips_key)
     val = None
     for kk in range(5):
         d = (normalize_tensor(f0[kk]) - normalize_tensor(f1[kk])) ** 2
+        if keep_masks is not None:
+            d = d * keep_masks[kk].to(d.dtype) * 2.0
         r = F.conv2d(d, sd[f"lin{kk}.model.1.weight"]).mean([2, 3], keepdim=True)  # utils.py:51-53,139-140
         val = r if val is None else val + r
     return val

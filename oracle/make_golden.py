@@ -246,6 +246,21 @@ def step_case():
     save(name, **res)
 
 
+def ckpt_case(name="ref_ckpt_step_small"):
+    """A checkpoint exactly as the reference writes it (vae_trainer.py:436-438,903-906): torch.save of the state_dict of
+    the DDP-wrapped reference VAE (keys prefixed `module.`), here for the step_small model so that the loaded drop-in must
+    reproduce that fixture's reconstruction."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    vae = ref_ae.VAE(resolution=32, in_channels=3, ch=32, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, z_channels=4,
+                     use_attn=False, decoder_also_perform_hr=False, use_wavelet=False)
+    vae.load_state_dict(seeded.fill_state_dict(vae.state_dict(), "step_small/vae"))
+    ddp = DDP(vae)
+    path = os.path.join(OUT, name + ".pt")
+    torch.save({k: v.half() if False else v for k, v in ddp.state_dict().items()}, path)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(ddp.state_dict()), "tensors")
+
+
 def _sub(tag, grads, res, keys, budget=60_000):
     """Full gradient tensors are too large for a fixture at ch=128: store every s-th element of the flattened tensor
     (s = smallest stride keeping <= budget elements; s == 1 keeps it whole) as `<tag>grad::<key>` and s as
@@ -377,7 +392,7 @@ if __name__ == "__main__":
     only = sys.argv[1:]
     if only:  # e.g. `python oracle/make_golden.py flux_step flux_hr` (the ch=128 cases take minutes of CPU time)
         for c in only:
-            {"flux_step": flux_step_case, "flux_hr": flux_hr_case}[c]()
+            {"flux_step": flux_step_case, "flux_hr": flux_hr_case, "ckpt": ckpt_case}[c]()
         dist.destroy_process_group()
         sys.exit(0)
     vae_case("vae_small", VO.VAEConfig(resolution=32, ch=32, ch_mult=(1, 2), num_res_blocks=2, z_channels=4), 2, 32)
@@ -391,5 +406,6 @@ if __name__ == "__main__":
     step_case()
     flux_step_case()
     flux_hr_case()
+    ckpt_case()
     dist.destroy_process_group()
     print("all golden fixtures written to", OUT)

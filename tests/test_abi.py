@@ -13,6 +13,7 @@ HEADER = os.path.join(ROOT, "include", "vqb200.h")
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#ifdef VQB_DEBUG.*?#endif", "", src, flags=re.S)  # bring-up symbols live in libvqb200_dbg.so only
     return sorted(set(re.findall(r"\b(vqb_[a-z0-9_]+)\s*\(", src)))
 
 

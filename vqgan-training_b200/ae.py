@@ -279,9 +279,15 @@ class Encoder(nn.Module):
                 nn.init.zeros_(module.bias)
 
     def forward(self, x) -> Tensor:
-        h = self.wavelet_transform(x)
-        fat = h.shape[1] <= 8 and ops.fat_conv_enabled()  # RGB input: 3 fat taps of 24 instead of 9 taps of 8 channels
-        a = Act(ops.to_nhwc(h, frame=fat), h.shape[1], framed=fat)
+        if self.use_wavelet and x.is_cuda and not x.requires_grad:
+            # wavelet analysis (utils.py:229-247) fused with the NCHW->NHWC conversion: one kernel, no fp32 intermediate
+            import utils as _u
+
+            a = Act(ops.wavelet_to_nhwc(x, _u.filters_expanded), 4 * x.shape[1])
+        else:
+            h = self.wavelet_transform(x)
+            fat = h.shape[1] <= 8 and ops.fat_conv_enabled()  # RGB input: 3 fat taps of 24, not 9 taps of 8 channels
+            a = Act(ops.to_nhwc(h, frame=fat), h.shape[1], framed=fat)
         a = self.conv_in.forward_act(a, want_stats=True)
         for i_level in range(self.num_resolutions):
             for i_block in range(self.num_res_blocks):

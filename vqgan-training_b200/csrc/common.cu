@@ -9,8 +9,12 @@ namespace vqb {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_launches{0};
+#ifdef VQB_DEBUG
 static std::atomic<int> g_debug{0};
 int debug_mode() { return g_debug.load(std::memory_order_relaxed); }
+#else
+int debug_mode() { return 0; }  // product build: the perf-experiment switches do not exist (see build_native.py --debug)
+#endif
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -120,6 +124,15 @@ const char* vqb_last_error(void) { return vqb::g_err; }
 int vqb_version(void) { return 100; }
 int vqb_device_ok(void) { return (vqb::device_is_sm100() && vqb::get_encode_fn() != nullptr) ? 1 : 0; }
 int vqb_kernel_launch_count(void) { return vqb::g_launches.load(std::memory_order_relaxed); }
-int vqb_set_debug_mode(int m) { vqb::g_debug.store(m); return 0; }
+int vqb_set_debug_mode(int m) {
+#ifdef VQB_DEBUG
+    vqb::g_debug.store(m);
+    return 0;
+#else
+    if (m != 0) return vqb::set_error(VQB_EINVAL, "vqb_set_debug_mode(%d): perf-experiment switches exist only in the "
+                                                  "-DVQB_DEBUG build (libvqb200_dbg.so)", m);
+    return 0;
+#endif
+}
 
 }  // extern "C"

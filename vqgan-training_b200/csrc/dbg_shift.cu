@@ -1,3 +1,4 @@
+#ifdef VQB_DEBUG  // bring-up experiment: only part of libvqb200_dbg.so (build_native.py --debug)
 // Bring-up experiment (not on the product path): does tcgen05.mma accept a 128B-swizzled K-major A operand whose
 // descriptor start is shifted by whole 128-byte rows inside a TMA-written tile, and whose 8-row groups are SBO bytes
 // apart for SBO not a multiple of 1024? This decides whether one activation halo tile in shared memory can serve all
@@ -101,3 +102,5 @@ extern "C" int vqb_dbg_shift_mma(const void* X, int R, const void* B, float* out
     VQB_CUDA(cudaGetLastError());
     return VQB_OK;
 }
+
+#endif  // VQB_DEBUG

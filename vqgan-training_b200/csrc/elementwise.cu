@@ -596,6 +596,47 @@ __global__ void wgrad_reduce_fold_kernel(const float* __restrict__ partial, floa
     }
 }
 
+
+// ------------------------------------------------------------------ wavelet front-end (utils.py:229-247)
+// y[n, ho, wo, c*4 + band] = sum_{i,j < 6} x[n, c, 2ho + i - 2, 2wo + j - 2] * filt[band][i][j]   (zero outside):
+// the reference's F.pad(2) + grouped 6x6 stride-2 conv, fused with the NCHW fp32 -> NHWC bf16 layout conversion the
+// encoder's first conv needs. One thread per output pixel; the 6x6 windows of neighbouring pixels overlap 9x, which the
+// L1/L2 absorbs (the whole input batch is a few tens of MB).
+__global__ void wavelet_fwd_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   const float* __restrict__ filt, int N, int C, int H, int W, int Cpad) {
+    __shared__ float f[4 * 36];
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) f[i] = filt[i];
+    __syncthreads();
+    const int Ho = H / 2, Wo = W / 2;
+    const int64_t total = static_cast<int64_t>(N) * Ho * Wo;
+    for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < total;
+         p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int wo = static_cast<int>(p % Wo), ho = static_cast<int>((p / Wo) % Ho);
+        const int64_t n = p / (static_cast<int64_t>(Wo) * Ho);
+        __nv_bfloat16* yp = y + p * Cpad;
+        for (int c = 0; c < C; ++c) {
+            const float* xp = x + (n * C + c) * static_cast<int64_t>(H) * W;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int h = 2 * ho + i - 2;
+                if (h < 0 || h >= H) continue;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int w = 2 * wo + j - 2;
+                    if (w < 0 || w >= W) continue;
+                    const float v = __ldg(xp + static_cast<int64_t>(h) * W + w);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[b] = fmaf(v, f[b * 36 + i * 6 + j], acc[b]);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) yp[c * 4 + b] = __float2bfloat16(acc[b]);
+        }
+        for (int c = 4 * C; c < Cpad; ++c) yp[c] = __float2bfloat16(0.f);
+    }
+}
+
 static inline int gs_blocks(int64_t total, int threads) {
     int64_t b = (total + threads - 1) / threads;
     const int64_t cap = static_cast<int64_t>(num_sms() > 0 ? num_sms() : 148) * 16;
@@ -804,6 +845,17 @@ int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, co
     }
     VQB_CUDA(cudaGetLastError());
     count_launch(3);
+    return VQB_OK;
+}
+
+int vqb_wavelet_fwd(const float* x, void* y, const float* filt, int N, int C, int H, int W, int Cpad, void* stream) {
+    VQB_CHECK(x && y && filt && H % 2 == 0 && W % 2 == 0 && Cpad % 8 == 0 && Cpad >= 4 * C,
+              "vqb_wavelet_fwd: bad arguments (H, W even; Cpad >= 4C, multiple of 8)");
+    const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2);
+    wavelet_fwd_kernel<<<gs_blocks(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<__nv_bfloat16*>(y), filt, N, C, H, W, Cpad);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
     return VQB_OK;
 }
 

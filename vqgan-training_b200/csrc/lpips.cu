@@ -101,11 +101,37 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const _
 }
 
 // ------------------------------------------------------------------ LPIPS tail
+// Train-mode dropout of NetLinLayer (utils.py:79-89: nn.Dropout(0.5) in front of the 1x1 lin conv; the reference never
+// puts LPIPS in eval mode, vae_trainer.py:477): element (n, p, c) of the squared-difference tensor is kept with
+// probability 1/2 and scaled by 2. The keep bit is a counter-based hash of (seed, flat NHWC element index) — the same
+// function in forward, backward and vqb_lpips_dropout_mask (which materialises it for parity tests); 32 consecutive
+// elements share one 64-bit mix (splitmix64 finaliser).
+__device__ __forceinline__ uint32_t dropout_word(uint64_t seed, uint64_t word) {
+    uint64_t z = seed + (word + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<uint32_t>(z >> 32);
+}
+// keep bits of the 8 consecutive elements starting at flat index e0 (e0 % 8 == 0), bit j = element e0 + j
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, int64_t e0) {
+    return (dropout_word(seed, static_cast<uint64_t>(e0) >> 5) >> (static_cast<uint32_t>(e0) & 31u)) & 0xFFu;
+}
+
+__global__ void lpips_dropout_mask_kernel(uint64_t seed, int64_t total8, uint8_t* __restrict__ mask) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total8;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t k = dropout_keep8(seed, i * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mask[i * 8 + j] = (k >> j) & 1u;
+    }
+}
+
 // A pixel is owned by G = min(32, C/8) lanes; each lane holds VPL = (C/8)/G 8-channel vectors of both features.
-template <int VPL>
+template <int VPL, bool DROP>
 __global__ void lpips_tail_fwd_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                       const float* __restrict__ w, float* __restrict__ out /* [N] */, int HW, int C,
-                                      int G, int pix_per_block, float inv_hw) {
+                                      int G, int pix_per_block, float inv_hw, uint64_t seed) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ppw = 32 / G;            // pixels per warp pass
     const int sub = lane / G;          // which pixel of the pass
@@ -147,12 +173,16 @@ __global__ void lpips_tail_fwd_kernel(const __nv_bfloat16* __restrict__ f0, cons
         const float i0 = 1.f / (sqrtf(s0) + 1e-10f), i1 = 1.f / (sqrtf(s1) + 1e-10f);
         float d = 0.f;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v)
+        for (int v = 0; v < VPL; ++v) {
+            uint32_t keep = 0xFFu;
+            if (DROP) keep = dropout_keep8(seed, (static_cast<int64_t>(n) * HW + p) * C + (gl + v * G) * 8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float t = a[v][j] * i0 - b[v][j] * i1;
-                d += wreg[v][j] * t * t;
+                const float wj = DROP ? (((keep >> j) & 1u) ? 2.f * wreg[v][j] : 0.f) : wreg[v][j];
+                d += wj * t * t;
             }
+        }
         if (ok) acc += d;
     }
     // block reduction of acc
@@ -168,11 +198,11 @@ __global__ void lpips_tail_fwd_kernel(const __nv_bfloat16* __restrict__ f0, cons
 }
 
 // d f0 = g[n]/HW * d val/d f0, gated by f0 > 0 (f0 is a post-ReLU VGG activation -> gradient of the pre-activation).
-template <int VPL>
+template <int VPL, bool DROP>
 __global__ void lpips_tail_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                       const float* __restrict__ w, const float* __restrict__ g /* [N] */,
                                       __nv_bfloat16* __restrict__ df0, int HW, int C, int G, int pix_per_block,
-                                      float inv_hw) {
+                                      float inv_hw, uint64_t seed) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ppw = 32 / G, sub = lane / G, gl = lane % G;
     const int n = blockIdx.y;
@@ -214,13 +244,17 @@ __global__ void lpips_tail_bwd_kernel(const __nv_bfloat16* __restrict__ f0, cons
         // q_c = 2 w_c (a_c i0 - b_c i1);  dot = sum_c q_c a_c
         float dot = 0.f;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v)
+        for (int v = 0; v < VPL; ++v) {
+            uint32_t keep = 0xFFu;
+            if (DROP) keep = dropout_keep8(seed, (static_cast<int64_t>(n) * HW + p) * C + (gl + v * G) * 8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float q = 2.f * wreg[v][j] * (a[v][j] * i0 - b[v][j] * i1);
+                const float wj = DROP ? (((keep >> j) & 1u) ? 2.f * wreg[v][j] : 0.f) : wreg[v][j];
+                const float q = 2.f * wj * (a[v][j] * i0 - b[v][j] * i1);
                 b[v][j] = q;  // reuse storage
                 dot += q * a[v][j];
             }
+        }
         for (int o = G >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
         // d f0_k = q_k i0 - dot * f0_k * i0^2 / ||f0||      (second term defined as 0 when ||f0|| == 0)
         const float k2 = nrm0 > 0.f ? dot * i0 * i0 / nrm0 : 0.f;
@@ -277,7 +311,8 @@ int vqb_maxpool2_bwd(const void* x, const void* dy, const void* add, void* dx, i
 
 // out[n] += (1/HW) sum_p sum_c w_c (f0/(|f0|+eps) - f1/(|f1|+eps))^2 ; out must be initialised by the caller
 // (the five LPIPS layers accumulate into the same [N] vector, utils.py:54-57).
-int vqb_lpips_tail_fwd(const void* f0, const void* f1, const float* w, float* out, int N, int HW, int C, void* stream) {
+static int lpips_tail_fwd_impl(const void* f0, const void* f1, const float* w, float* out, int N, int HW, int C,
+                               bool drop, uint64_t seed, void* stream) {
     VQB_CHECK(f0 && f1 && w && out, "vqb_lpips_tail_fwd: null pointer");
     VQB_CHECK(C % 64 == 0 && C <= 512 && ((C / 8) <= 32 || (C / 8) % 32 == 0), "vqb_lpips_tail_fwd: C=%d unsupported", C);
     const int V = C / 8, G = V < 32 ? V : 32, VPL = V / G;
@@ -290,10 +325,14 @@ int vqb_lpips_tail_fwd(const void* f0, const void* f1, const float* w, float* ou
     const float inv = 1.f / static_cast<float>(HW);
     const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(f0);
     const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(f1);
-    if (VPL == 1)
-        lpips_tail_fwd_kernel<1><<<grid, 256, 0, st>>>(a, b, w, out, HW, C, G, ppb, inv);
+    if (VPL == 1 && !drop)
+        lpips_tail_fwd_kernel<1, false><<<grid, 256, 0, st>>>(a, b, w, out, HW, C, G, ppb, inv, seed);
+    else if (VPL == 2 && !drop)
+        lpips_tail_fwd_kernel<2, false><<<grid, 256, 0, st>>>(a, b, w, out, HW, C, G, ppb, inv, seed);
+    else if (VPL == 1)
+        lpips_tail_fwd_kernel<1, true><<<grid, 256, 0, st>>>(a, b, w, out, HW, C, G, ppb, inv, seed);
     else if (VPL == 2)
-        lpips_tail_fwd_kernel<2><<<grid, 256, 0, st>>>(a, b, w, out, HW, C, G, ppb, inv);
+        lpips_tail_fwd_kernel<2, true><<<grid, 256, 0, st>>>(a, b, w, out, HW, C, G, ppb, inv, seed);
     else
         return set_error(VQB_EINVAL, "vqb_lpips_tail_fwd: C=%d unsupported", C);
     VQB_CUDA(cudaGetLastError());
@@ -301,8 +340,24 @@ int vqb_lpips_tail_fwd(const void* f0, const void* f1, const float* w, float* ou
     return VQB_OK;
 }
 
-int vqb_lpips_tail_bwd(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW, int C,
-                       void* stream) {
+int vqb_lpips_tail_fwd(const void* f0, const void* f1, const float* w, float* out, int N, int HW, int C, void* stream) {
+    return lpips_tail_fwd_impl(f0, f1, w, out, N, HW, C, false, 0, stream);
+}
+int vqb_lpips_tail_fwd_dropout(const void* f0, const void* f1, const float* w, float* out, int N, int HW, int C,
+                               uint64_t seed, void* stream) {
+    return lpips_tail_fwd_impl(f0, f1, w, out, N, HW, C, true, seed, stream);
+}
+int vqb_lpips_dropout_mask(uint64_t seed, int N, int HW, int C, uint8_t* mask, void* stream) {
+    VQB_CHECK(mask && C % 8 == 0, "vqb_lpips_dropout_mask: bad arguments");
+    const int64_t total8 = static_cast<int64_t>(N) * HW * C / 8;
+    lpips_dropout_mask_kernel<<<gs_blocks2(total8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, total8, mask);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+static int lpips_tail_bwd_impl(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW,
+                               int C, bool drop, uint64_t seed, void* stream) {
     VQB_CHECK(f0 && f1 && w && g && df0, "vqb_lpips_tail_bwd: null pointer");
     VQB_CHECK(C % 64 == 0 && C <= 512, "vqb_lpips_tail_bwd: C=%d unsupported", C);
     const int V = C / 8, G = V < 32 ? V : 32, VPL = V / G;
@@ -315,15 +370,29 @@ int vqb_lpips_tail_bwd(const void* f0, const void* f1, const float* w, const flo
     const float inv = 1.f / static_cast<float>(HW);
     const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(f0);
     const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(f1);
-    if (VPL == 1)
-        lpips_tail_bwd_kernel<1><<<grid, 256, 0, st>>>(a, b, w, g, static_cast<__nv_bfloat16*>(df0), HW, C, G, ppb, inv);
+    __nv_bfloat16* d = static_cast<__nv_bfloat16*>(df0);
+    if (VPL == 1 && !drop)
+        lpips_tail_bwd_kernel<1, false><<<grid, 256, 0, st>>>(a, b, w, g, d, HW, C, G, ppb, inv, seed);
+    else if (VPL == 2 && !drop)
+        lpips_tail_bwd_kernel<2, false><<<grid, 256, 0, st>>>(a, b, w, g, d, HW, C, G, ppb, inv, seed);
+    else if (VPL == 1)
+        lpips_tail_bwd_kernel<1, true><<<grid, 256, 0, st>>>(a, b, w, g, d, HW, C, G, ppb, inv, seed);
     else if (VPL == 2)
-        lpips_tail_bwd_kernel<2><<<grid, 256, 0, st>>>(a, b, w, g, static_cast<__nv_bfloat16*>(df0), HW, C, G, ppb, inv);
+        lpips_tail_bwd_kernel<2, true><<<grid, 256, 0, st>>>(a, b, w, g, d, HW, C, G, ppb, inv, seed);
     else
         return set_error(VQB_EINVAL, "vqb_lpips_tail_bwd: C=%d unsupported", C);
     VQB_CUDA(cudaGetLastError());
     count_launch();
     return VQB_OK;
+}
+
+int vqb_lpips_tail_bwd(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW, int C,
+                       void* stream) {
+    return lpips_tail_bwd_impl(f0, f1, w, g, df0, N, HW, C, false, 0, stream);
+}
+int vqb_lpips_tail_bwd_dropout(const void* f0, const void* f1, const float* w, const float* g, void* df0, int N, int HW,
+                               int C, uint64_t seed, void* stream) {
+    return lpips_tail_bwd_impl(f0, f1, w, g, df0, N, HW, C, true, seed, stream);
 }
 
 }  // extern "C"

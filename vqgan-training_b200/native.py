@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libvqb200.so")
+# VQB_DEBUG_LIB=1 selects the -DVQB_DEBUG build (perf-experiment switches + bring-up kernels; build_native.py --debug)
+_LIB_PATH = os.path.join(_HERE, "libvqb200_dbg.so" if os.environ.get("VQB_DEBUG_LIB", "0") == "1" else "libvqb200.so")
 
 VQB_MAX_VIEWS = 16
 VQB_MAX_TAPS = 16
@@ -86,6 +87,7 @@ def load():
         "vqb_gn_silu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
         "vqb_gn_silu_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "vqb_dbg_shift_mma": (i32, [vp, i32, vp, vp, i32, i32, i32, vp]),
+        "vqb_wavelet_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "vqb_upsample2x_fwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vqb_upsample2x_bwd": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vqb_colsum": (i32, [vp, vp, i64, i32, vp]),
@@ -94,6 +96,9 @@ def load():
         "vqb_maxpool2_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "vqb_lpips_tail_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
         "vqb_lpips_tail_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "vqb_lpips_tail_fwd_dropout": (i32, [vp, vp, vp, vp, i32, i32, i32, C.c_uint64, vp]),
+        "vqb_lpips_tail_bwd_dropout": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, C.c_uint64, vp]),
+        "vqb_lpips_dropout_mask": (i32, [C.c_uint64, i32, i32, i32, vp, vp]),
         "vqb_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, vp]),
         "vqb_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "vqb_set_debug_mode": (i32, [i32]),

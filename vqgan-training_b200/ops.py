@@ -422,6 +422,21 @@ def fat_conv_enabled() -> bool:
     return _fat_state["ok"]
 
 
+def wavelet_to_nhwc(x: torch.Tensor, filt: torch.Tensor) -> torch.Tensor:
+    """[N,C,H,W] fp32 image -> [N,H/2,W/2,cpad(4C)] bf16: the wavelet front-end (utils.py:229-247) fused with the layout
+    conversion. Input-side op: the image is data, so there is no backward."""
+    require_cuda(x)
+    if x.requires_grad:
+        raise RuntimeError("wavelet front-end: the input image must not require grad (input-side op without backward)")
+    x = x.detach().float().contiguous()
+    N, C, H, W = x.shape
+    Cp = plans.cpad(4 * C)
+    y = torch.empty(N, H // 2, W // 2, Cp, device=x.device, dtype=torch.bfloat16)
+    f = filt.detach().to(device=x.device, dtype=torch.float32).reshape(4, 36).contiguous()
+    check(_L().vqb_wavelet_fwd(ptr(x), ptr(y), ptr(f), N, C, H, W, Cp, stream_ptr()), "wavelet_fwd")
+    return y
+
+
 def to_nhwc(x, shift=None, inv_scale=None, frame=False):
     return ToNHWC.apply(x, shift, inv_scale, frame)
 
@@ -802,17 +817,24 @@ def maxpool2(x):
 
 
 class LpipsTailFn(torch.autograd.Function):
-    """One LPIPS layer (utils.py:46-53,134-140): unit-normalise over channels, squared difference, 1x1 lin, spatial
-    mean -> [N]. Gradient only w.r.t. f0 (reconstruction branch), gated by f0 > 0 (post-ReLU feature)."""
+    """One LPIPS layer (utils.py:46-53,134-140): unit-normalise over channels, squared difference, [train mode: Dropout(0.5)
+    with the counter-based mask of `seed`], 1x1 lin, spatial mean -> [N]. Gradient only w.r.t. f0 (reconstruction branch),
+    gated by f0 > 0 (post-ReLU feature)."""
 
     @staticmethod
-    def forward(ctx, f0, f1, w):
+    def forward(ctx, f0, f1, w, seed):
         f0, f1 = f0.contiguous(), f1.contiguous()
         N, H, W, C = f0.shape
         out = torch.zeros(N, device=f0.device, dtype=torch.float32)
         wv = w.detach().reshape(-1).float().contiguous()
-        check(_L().vqb_lpips_tail_fwd(ptr(f0), ptr(f1), ptr(wv), ptr(out), N, H * W, C, stream_ptr()), "lpips_tail_fwd")
+        if seed is None:
+            check(_L().vqb_lpips_tail_fwd(ptr(f0), ptr(f1), ptr(wv), ptr(out), N, H * W, C, stream_ptr()),
+                  "lpips_tail_fwd")
+        else:
+            check(_L().vqb_lpips_tail_fwd_dropout(ptr(f0), ptr(f1), ptr(wv), ptr(out), N, H * W, C, seed, stream_ptr()),
+                  "lpips_tail_fwd_dropout")
         ctx.save_for_backward(f0, f1, wv)
+        ctx.seed = seed
         return out
 
     @staticmethod
@@ -821,13 +843,24 @@ class LpipsTailFn(torch.autograd.Function):
         N, H, W, C = f0.shape
         g = g.float().contiguous()
         df0 = torch.empty_like(f0)
-        check(_L().vqb_lpips_tail_bwd(ptr(f0), ptr(f1), ptr(wv), ptr(g), ptr(df0), N, H * W, C, stream_ptr()),
-              "lpips_tail_bwd")
-        return df0, None, None
+        if ctx.seed is None:
+            check(_L().vqb_lpips_tail_bwd(ptr(f0), ptr(f1), ptr(wv), ptr(g), ptr(df0), N, H * W, C, stream_ptr()),
+                  "lpips_tail_bwd")
+        else:
+            check(_L().vqb_lpips_tail_bwd_dropout(ptr(f0), ptr(f1), ptr(wv), ptr(g), ptr(df0), N, H * W, C, ctx.seed,
+                                                  stream_ptr()), "lpips_tail_bwd_dropout")
+        return df0, None, None, None
 
 
-def lpips_tail(f0, f1, w):
-    return LpipsTailFn.apply(f0, f1, w)
+def lpips_tail(f0, f1, w, dropout_seed=None):
+    return LpipsTailFn.apply(f0, f1, w, dropout_seed)
+
+
+def lpips_dropout_mask(seed: int, N: int, HW: int, C: int, device) -> torch.Tensor:
+    """The keep mask ([N, HW, C] uint8) the train-mode LPIPS tail kernels use for `seed` (parity tests)."""
+    m = torch.empty(N, HW, C, device=device, dtype=torch.uint8)
+    check(_L().vqb_lpips_dropout_mask(seed, N, HW, C, ptr(m), stream_ptr()), "lpips_dropout_mask")
+    return m
 
 
 def vq_argmin(z_flat: torch.Tensor, codebook: torch.Tensor):

@@ -33,16 +33,39 @@ from torchvision import models
 import ops
 
 
+def _offline() -> bool:
+    """VQB_OFFLINE=1 is the explicit opt-in (tests, benchmarks, smoke) to run with random-initialised VGG16 / LPIPS lin
+    weights. Without it a missing pretrained file is an ERROR: silently training against a random perceptual metric
+    (whose uniform(-b, b) lin weights can be driven down by *increasing* feature differences) is never what a run wants."""
+    return os.environ.get("VQB_OFFLINE", "0") == "1"
+
+
 def _torchvision_vgg16_features(pretrained: bool):
-    """utils.py:95,148 call models.vgg16(pretrained=True); keep that call (so the usual monkey-patches apply) but
-    survive a machine without network access."""
-    if os.environ.get("VQB_OFFLINE", "0") == "1":  # tests / benchmarks: never touch the network
+    """utils.py:95,148 call models.vgg16(pretrained=True); keep that call (so the usual monkey-patches apply)."""
+    if _offline():  # never touch the network
         return models.vgg16(weights=None).features
     try:
         return models.vgg16(pretrained=pretrained).features
     except Exception as e:  # URLError etc.
-        warnings.warn(f"torchvision VGG16 weights unavailable ({type(e).__name__}: {e}); using random init")
-        return models.vgg16(weights=None).features
+        raise RuntimeError(f"torchvision VGG16 ImageNet weights unavailable ({type(e).__name__}: {e}). Provide them in "
+                           "the torch hub cache, or set VQB_OFFLINE=1 to run with random-initialised VGG16 weights "
+                           "(tests / benchmarks only)") from e
+
+
+VGG_LPIPS_URL = "https://heibox.uni-heidelberg.de/seafhttp/files/9535cbee-6558-4c0c-8743-78f5e56ea75e/vgg.pth"
+
+
+def broadcast_module_state(module: nn.Module, src: int = 0):
+    """Frozen modules (LPIPS and its VGG trunk) are not DDP-wrapped: make every rank use rank `src`'s weights, so that a
+    per-rank difference in what could be loaded can never make ranks optimise different objectives."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)
+    if any(p.is_cuda for p in module.parameters()):
+        ops.weights_updated(list(module.parameters()))
 
 
 def _as_b200_conv(layer: nn.Conv2d):
@@ -95,21 +118,35 @@ class LPIPS(nn.Module):
         self.load_from_pretrained()
         for param in self.parameters():
             param.requires_grad = False
+        self.dropout_seeds = None       # test hook: five fixed per-layer seeds for the train-mode dropout masks
+        self.last_dropout_seeds = None
 
     def load_from_pretrained(self, name="vgg_lpips"):
+        """utils.py:25-37: ./vgg.pth, else download it (same URL), else fail — unless VQB_OFFLINE=1."""
+        if _offline() and not os.path.exists("vgg.pth"):
+            return
         try:
             data = torch.load("vgg.pth", map_location=torch.device("cpu"))
         except Exception:
-            warnings.warn("vgg.pth (LPIPS linear weights) not found and cannot be downloaded here; keeping the "
-                          "random-initialised lin layers")
-            return
+            print("Failed to load vgg.pth, downloading...")
+            try:
+                import urllib.request
+
+                urllib.request.urlretrieve(VGG_LPIPS_URL, "vgg.pth")
+                data = torch.load("vgg.pth", map_location=torch.device("cpu"))
+            except Exception as e:
+                raise RuntimeError(f"vgg.pth (LPIPS linear weights) is missing and could not be downloaded ({e}); place "
+                                   "it in the working directory, or set VQB_OFFLINE=1 to run with random lin layers "
+                                   "(tests / benchmarks only)") from e
         self.load_state_dict(data, strict=False)
 
     def forward(self, input, target):
         from ae import Act
 
-        # NOTE: the reference leaves this module in train mode, so its nn.Dropout(0.5) in front of
-        # every lin layer is active during training. The fused tail implements eval-mode semantics.
+        # SURVEY.md fact 5: the reference never calls .eval() on LPIPS, so its nn.Dropout(0.5) in front of every lin layer
+        # is live during training. Honoured here: in train mode (and when the lin layer has a Dropout) the fused tail
+        # applies a counter-based keep mask; the per-call seed comes from torch's CPU generator (torch.manual_seed
+        # reproducible, no device sync). `dropout_seeds` (test hook) pins the five per-layer seeds.
         fat = ops.fat_conv_enabled()
         a0 = Act(self.scaling_layer.to_act(input, fat), 3, framed=fat)
         with torch.no_grad():
@@ -118,8 +155,14 @@ class LPIPS(nn.Module):
         outs0 = self.net.forward_acts(a0)
         lins = [self.lin0, self.lin1, self.lin2, self.lin3, self.lin4]
         val = None
+        seeds = [None] * 5
+        if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.lin0.model):
+            seeds = self.dropout_seeds
+            if seeds is None:
+                seeds = [int(v) for v in torch.randint(0, 2 ** 62, (5,), dtype=torch.int64)]
+            self.last_dropout_seeds = list(seeds)
         for kk in range(len(self.chns)):
-            r = ops.lpips_tail(outs0[kk].t, outs1[kk].t, lins[kk].model[-1].weight)
+            r = ops.lpips_tail(outs0[kk].t, outs1[kk].t, lins[kk].model[-1].weight, seeds[kk])
             val = r if val is None else val + r
         return val.reshape(-1, 1, 1, 1)
 

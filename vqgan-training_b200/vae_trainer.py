@@ -314,6 +314,68 @@ def cosine_with_warmup(optimizer, num_warmup_steps, num_training_steps):
     return optim.lr_scheduler.LambdaLR(optimizer, f)
 
 
+def latent_augment(z, z_s, real_images_hr, flip_invariance, crop_invariance, downscale_factor=16,
+                   decoder_also_perform_hr=False):
+    """vae_trainer.py:567-621, the equivariance augmentations between encoder and decoder. Draw order of python's
+    `random` is the reference's (three `random.random()` draws always happen; the crop's four `randint`s only when it
+    fires):
+      * horizontal flip of the latent with channels [-4:-2] negated + the same flip of the target image,
+      * vertical flip with channels [-2:] negated,
+      * a random crop of the latent (>= 12 latent pixels per side) and the matching crop of the target image.
+    -> (z_s, real_images_hr)."""
+    if random.random() < 0.5 and flip_invariance:  # :567-570
+        z_s = torch.flip(z_s, [-1]).clone()
+        z_s[:, -4:-2] = -z_s[:, -4:-2]
+        real_images_hr = torch.flip(real_images_hr, [-1])
+    if random.random() < 0.5 and flip_invariance:  # :572-575
+        z_s = torch.flip(z_s, [-2]).clone()
+        z_s[:, -2:] = -z_s[:, -2:]
+        real_images_hr = torch.flip(real_images_hr, [-2])
+    if random.random() < 0.5 and crop_invariance:  # :577-621
+        z_h, z_w = z.shape[-2:]
+        new_z_h, new_z_w = random.randint(12, z_h - 1), random.randint(12, z_w - 1)
+        offset_z_h, offset_z_w = random.randint(0, z_h - new_z_h - 1), random.randint(0, z_w - new_z_w - 1)
+        f = downscale_factor * (2 if decoder_also_perform_hr else 1)
+        real_images_hr = real_images_hr[:, :, offset_z_h * f:(offset_z_h + new_z_h) * f,
+                                        offset_z_w * f:(offset_z_w + new_z_w) * f]
+        z_s = z_s[:, :, offset_z_h:offset_z_h + new_z_h, offset_z_w:offset_z_w + new_z_w]
+        assert real_images_hr.shape[-2:] == (new_z_h * f, new_z_w * f) and z_s.shape[-2:] == (new_z_h, new_z_w)
+    return z_s, real_images_hr
+
+
+def load_vae_checkpoint(vae_ddp: nn.Module, path_or_state):
+    """vae_trainer.py:505-513: strict load of a `module.`-prefixed VAE checkpoint (what the reference saves at :903-906);
+    on failure the `_orig_mod.` infixes a torch.compile'd encoder/decoder leaves in the keys are stripped and the strict
+    load is retried. After loading, the cached bf16 GEMM operands are refreshed."""
+    state_dict = torch.load(path_or_state, map_location="cpu") if isinstance(path_or_state, (str, os.PathLike)) \
+        else path_or_state
+    try:
+        status = vae_ddp.load_state_dict(state_dict, strict=True)
+    except Exception as e:
+        print(e)
+        state_dict = {k.replace("_orig_mod.", ""): v for k, v in state_dict.items()}
+        status = vae_ddp.load_state_dict(state_dict, strict=True)
+        print(status)
+    if any(p.is_cuda for p in vae_ddp.parameters()):
+        import ops
+
+        ops.weights_updated(list(vae_ddp.parameters()))
+    return status
+
+
+def make_image_grid(images: torch.Tensor, D: int) -> torch.Tensor:
+    """vae_trainer.py:872-893: the first 8 images, cropped to D x D, tiled 2 rows x 4 columns into a (3, 4D, 4D) canvas
+    (the reference allocates 4D x 4D and fills the top half)."""
+    canvas = torch.zeros((3, D * 4, D * 4))
+    images = images[:, :, :D, :D].cpu()
+    for i in range(2):
+        for j in range(4):
+            if i * 4 + j < images.shape[0]:
+                img = images[i * 4 + j]
+                canvas[:, i * D:i * D + img.shape[-2], j * D:j * D + img.shape[-1]] = img
+    return canvas
+
+
 class Trainer:
     """One object = the state of vae_trainer.py:422-522 (models, optimizers, scheduler, LeCam anchors); `.step(batch)`
     = one iteration of the loop body :530-708. bench.py and the tests drive this same public class."""
@@ -368,6 +430,9 @@ class Trainer:
         self.vae.attach_store(self.optimizer_G.store)
         self.discriminator.attach_store(self.optimizer_D.store)
         self.lpips = LPIPS().to(device)
+        from utils import broadcast_module_state
+
+        broadcast_module_state(self.lpips)  # frozen, not DDP-wrapped: every rank must score with rank 0's weights
         if lpips_eval:
             self.lpips.eval()
         self.lr_scheduler = cosine_with_warmup(self.optimizer_G, 200, max_steps)
@@ -399,22 +464,8 @@ class Trainer:
         else:
             z_s = vae.module.reg(z)
 
-        if random.random() < 0.5 and self.flip_invariance:  # :567-570
-            z_s = torch.flip(z_s, [-1]).clone()
-            z_s[:, -4:-2] = -z_s[:, -4:-2]
-            real_images_hr = torch.flip(real_images_hr, [-1])
-        if random.random() < 0.5 and self.flip_invariance:  # :572-575
-            z_s = torch.flip(z_s, [-2]).clone()
-            z_s[:, -2:] = -z_s[:, -2:]
-            real_images_hr = torch.flip(real_images_hr, [-2])
-        if random.random() < 0.5 and self.crop_invariance:  # :577-621
-            z_h, z_w = z.shape[-2:]
-            new_z_h, new_z_w = random.randint(12, z_h - 1), random.randint(12, z_w - 1)
-            offset_z_h, offset_z_w = random.randint(0, z_h - new_z_h - 1), random.randint(0, z_w - new_z_w - 1)
-            f = self.downscale_factor * (2 if self.decoder_also_perform_hr else 1)
-            real_images_hr = real_images_hr[:, :, offset_z_h * f:(offset_z_h + new_z_h) * f,
-                                            offset_z_w * f:(offset_z_w + new_z_w) * f]
-            z_s = z_s[:, :, offset_z_h:offset_z_h + new_z_h, offset_z_w:offset_z_w + new_z_w]
+        z_s, real_images_hr = latent_augment(z, z_s, real_images_hr, self.flip_invariance, self.crop_invariance,
+                                             self.downscale_factor, self.decoder_also_perform_hr)  # :567-621
         real_images_hr = real_images_hr.contiguous()
 
         reconstructed = vae.module.decoder(z_s.contiguous())  # :623-624
@@ -487,6 +538,38 @@ class Trainer:
                    loss_data=loss_data, z=z_for_stats, reconstructed=reconstructed.detach())
         self.last = out
         return out
+
+    @torch.no_grad()
+    def evaluate(self, test_batches, max_batches=2):
+        """vae_trainer.py:811-893 (rank 0): encode the 256^2 area-resized test images, clamp, reg, [flip_invariance: decode
+        the (-1,-2)-flipped latent with its last four channels negated and flip the image back, :837-861], decode,
+        un-normalise to [0,1]. -> (test grid, reconstruction grid) as (3, 4D, 4D) tensors + the raw tensors."""
+        vae = self.vae
+        all_test, all_rec = [], []
+        for batch in test_batches:
+            ori = (batch[0] if isinstance(batch, (tuple, list)) else batch).to(self.device)
+            x = F.interpolate(ori, size=(256, 256), mode="area") if ori.shape[-2:] != (256, 256) else ori
+            z = vae.module.encoder(x)
+            if self.do_clamp:
+                z = z.clamp(-self.clamp_th, self.clamp_th)
+            z_s = vae.module.reg(z)
+            if isinstance(z_s, tuple):
+                z_s = z_s[0]
+            if self.flip_invariance:
+                z_s = torch.flip(z_s, [-1, -2]).clone()
+                z_s[:, -4:] = -z_s[:, -4:]
+            rec = vae.module.decoder(z_s.contiguous())
+            ori, rec = (ori * 0.5 + 0.5).clamp(0, 1), (rec * 0.5 + 0.5).clamp(0, 1)
+            if self.flip_invariance:
+                rec = torch.flip(rec, [-1, -2])
+            all_test.append(ori)
+            all_rec.append(rec)
+            if len(all_test) >= max_batches:
+                break
+        test_images, reconstructed = torch.cat(all_test, 0), torch.cat(all_rec, 0)
+        D = 512 if self.decoder_also_perform_hr else 256
+        return {"test_images": make_image_grid(test_images, D), "reconstructed_test_images":
+                make_image_grid(reconstructed, D), "raw_test": test_images, "raw_reconstructed": reconstructed}
 
     def z_quantiles(self, z):
         """vae_trainer.py:541-559, evaluated only when something is logged."""
@@ -574,17 +657,14 @@ def train_ddp(dataset_url, test_dataset_url, num_epochs, batch_size, do_ganloss,
         logger.addHandler(handler)
 
     if load_path is not None:  # :505-513
-        state_dict = torch.load(load_path, map_location="cpu")
-        try:
-            tr.vae.load_state_dict(state_dict, strict=True)
-        except Exception as e:
-            print(e)
-            state_dict = {k.replace("_orig_mod.", ""): v for k, v in state_dict.items()}
-            print(tr.vae.load_state_dict(state_dict, strict=True))
+        load_vae_checkpoint(tr.vae, load_path)
 
     dataloader = create_dataloader(dataset_url, batch_size, num_workers=4, do_shuffle=True)
+    test_dataloader = create_dataloader(test_dataset_url, batch_size, num_workers=4, do_shuffle=False, just_resize=True)
     if isinstance(dataloader, SyntheticLoader) and not decoder_also_perform_hr:
         dataloader = SyntheticLoader(batch_size, 256)  # 256^2 "hr" images: the only shape-consistent non-HR recipe
+    if isinstance(test_dataloader, SyntheticLoader):
+        test_dataloader = SyntheticLoader(batch_size, 512 if decoder_also_perform_hr else 256, seed=7, n_distinct=2)
     t0 = time.time()
     done = False
     for epoch in range(num_epochs):
@@ -619,8 +699,15 @@ def train_ddp(dataset_url, test_dataset_url, num_epochs, batch_size, do_ganloss,
                     wandb.log({k: v for k, v in items})
             t0 = time.time()
             if evaluate_every_n_steps > 0 and tr.global_step % evaluate_every_n_steps == 1 and master_process:
+                ev = tr.evaluate(test_dataloader)  # :811-893: reconstruction grids of (up to) 8 test images
+                logger.info(f"Epoch [{epoch}/{num_epochs}] - Logging test images")
+                if use_wandb:
+                    wandb.log({"reconstructed_test_images": [wandb.Image(ev["reconstructed_test_images"])],
+                               "test_images": [wandb.Image(ev["test_images"])]})
                 os.makedirs(f"./ckpt/{run_name}", exist_ok=True)  # :903-910: VAE weights only, DDP-prefixed keys
-                torch.save(tr.vae.state_dict(), f"./ckpt/{run_name}/vae_epoch_{epoch}_step_{tr.global_step}.pt")
+                ck = f"./ckpt/{run_name}/vae_epoch_{epoch}_step_{tr.global_step}.pt"
+                torch.save(tr.vae.state_dict(), ck)
+                print(f"Saved checkpoint to {ck}")
         if done:
             break
     cleanup()
