@@ -123,11 +123,14 @@ def _peer_step(vsd, lsd, dsd, real, gan, all_bf16=False):
             z = z.float().clamp(-8.0, 8.0)
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 recon = VO.decoder_forward(osd, VO.reg(z), CFG)
-            percep = LP.lpips_forward(lsd_c, LO.gradnorm(recon, 1.0), real).mean()
+            with torch.autocast("cuda", dtype=torch.bfloat16):  # LPIPS and D trunks in bf16 as well
+                percep = LP.lpips_forward(lsd_c, LO.gradnorm(recon, 1.0), real).float().mean()
             vl, _ = LO.vae_loss_function(real, LO.gradnorm(recon, 0.001), z, do_pool=True, do_recon=False)
             loss = percep + vl
             if gan:
-                loss = loss + LO.gan_gen_loss(LP.patchd_forward(dsd_c, LO.gradnorm(recon, 1.0)), "hinge")
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    fake = LP.patchd_forward(dsd_c, LO.gradnorm(recon, 1.0))
+                loss = loss + LO.gan_gen_loss(fake.float(), "hinge")
             loss.backward()
             o = {"loss": loss.detach(), "percep": percep.detach(), "z": z.detach(), "recon": recon.detach()}
         else:
@@ -203,7 +206,10 @@ def test_flux_generator_step_vs_reference_golden(flux_models, gan, batch):
     # everything downstream of the decoder: bounded by the reference's own precision mix
     assert _bound(ez, Bf["ez"], 5e-3), "z"
     assert _bound(er, M["er"], 1e-2), "recon"
-    assert _bound(ep, M["ep"], 5e-3) and _bound(el, max(M["el"], Bf["el"]), 1e-2), "losses"
+    # the GAN term is a mean over 256 patch logits whose bf16 errors are spatially coherent (weight rounding acts on
+    # positive post-ReLU features): the mean inherits the per-logit error level, 1.5e-2 for this implementation AND for
+    # eager bf16 D (test_flux_discriminator_step...), hence the 2e-2 floor with the GAN term, 5e-3 without
+    assert _bound(ep, M["ep"], 5e-3) and _bound(el, max(M["el"], Bf["el"]), 2e-2 if gan else 5e-3), "losses"
     assert _bound(nr_dec.max(), M["nr_dec"].max(), 0.02) and _bound(nr_dec.mean(), M["nr_dec"].mean(), 0.01), "dec norms"
     if batch == 1:
         assert _bound(nr_enc.max(), Bf["nr_enc"].max(), 0.02) and _bound(nr_enc.mean(), Bf["nr_enc"].mean(), 0.01), \

@@ -330,3 +330,55 @@ def test_wavelet_front_end_kernel_vs_reference_golden():
     z_fused = enc(xi)
     z_aten = enc(xi.clone().requires_grad_(True))  # requires_grad input takes the ATen wavelet path
     assert rel_l2(z_fused, z_aten) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 128, 128), (2, 16, 16, 256, 512), (1, 64, 64, 128, 256), (3, 16, 32, 512, 256)])
+def test_fused_groupnorm_backward_statistics_in_dgrad_epilogue(shape):
+    """The data-gradient launch of the conv that consumes swish(GroupNorm(x)) accumulates (sum du, sum du*xhat) in its
+    epilogue (vqb_conv_gemm_gnbwd) and the GroupNorm backward skips its reduction pass. Checked (a) against the unfused
+    path (same kernels otherwise) and (b) against fp32 PyTorch autograd of the same block on the same bf16-rounded
+    inputs, for dx, dgamma, dbeta and the conv's weight gradient; the fused path must actually have been taken."""
+    import ae
+    import native
+    import ops
+    import torch.nn.functional as F
+
+    N, H, W, Cin, Cout = shape
+    torch.manual_seed(0)
+    norm = ae.FP32GroupNorm(32, Cin, eps=1e-6, affine=True).cuda()
+    conv = ae.StandardizedC2d(Cin, Cout, kernel_size=3, stride=1, padding=1).cuda()
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.2)
+        norm.bias.normal_(0.0, 0.2)
+    x0 = (torch.randn(N, H, W, Cin, device="cuda") * 1.5 + 0.3).to(torch.bfloat16)
+    gy = torch.randn(N, H, W, Cout, device="cuda").to(torch.bfloat16)
+    res = {}
+    for fuse in (True, False):
+        ops._GN_BWD_FUSE = fuse
+        for p_ in list(norm.parameters()) + list(conv.parameters()):
+            p_.grad = None
+        x = x0.clone().requires_grad_(True)
+        a = ae.Act(x, Cin)
+        h, skip = norm.forward_with_skip(a, silu=True)
+        l0 = native.launch_count()
+        y = conv.forward_act(h)
+        (y.t.float() * gy.float()).sum().backward()
+        res[fuse] = (x.grad.float().clone(), norm.weight.grad.clone(), norm.bias.grad.clone(), conv.weight.grad.clone())
+        res[("launches", fuse)] = native.launch_count() - l0
+    ops._GN_BWD_FUSE = True
+    assert res[("launches", True)] == res[("launches", False)] - 1, "the fused path was not taken"
+    # fp32 reference
+    xr = x0.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    gw, gb = norm.weight.detach().clone().requires_grad_(True), norm.bias.detach().clone().requires_grad_(True)
+    cw = conv.weight.detach().to(torch.bfloat16).float().requires_grad_(True)
+    hh = F.group_norm(xr, 32, gw, gb, 1e-6)
+    hh = (hh * torch.sigmoid(hh)).to(torch.bfloat16).float()  # the stored activation is bf16
+    yy = F.conv2d(hh, cw, conv.bias.detach(), padding=1)
+    (yy * gy.float().permute(0, 3, 1, 2)).sum().backward()
+    ref = (xr.grad.permute(0, 2, 3, 1), gw.grad, gb.grad, cw.grad)
+    names = ("dx", "dgamma", "dbeta", "dW")
+    for i, nm in enumerate(names):
+        e_fu = rel_l2(res[True][i], res[False][i])
+        e_f, e_u = rel_l2(res[True][i], ref[i]), rel_l2(res[False][i], ref[i])
+        print(f"  {shape} {nm}: fused vs unfused {e_fu:.2e}; vs fp32 torch: fused {e_f:.2e} unfused {e_u:.2e}")
+        assert e_fu < 5e-3 and e_f < max(1.3 * e_u, 1e-2), nm

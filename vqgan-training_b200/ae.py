@@ -40,11 +40,13 @@ from utils import wavelet_transform_multi_channel
 class Act:
     """Internal activation: bf16 NHWC tensor `t` [N,H,W,Cp] carrying its true channel count `C`."""
 
-    __slots__ = ("t", "C", "stats", "framed")
+    __slots__ = ("t", "C", "stats", "framed", "link")
 
-    def __init__(self, t: Tensor, C: int, stats=None, framed=False):
+    def __init__(self, t: Tensor, C: int, stats=None, framed=False, link=None):
         self.t = t
         self.C = C
+        self.link = link  # ops.GnLink when t is the output of a GroupNorm(+swish): lets the consuming conv's data-gradient
+        # epilogue accumulate that GroupNorm's backward statistics
         self.stats = stats  # per-(n, channel) sum / sum of squares [N, C, 2] when the producing conv computed them
         self.framed = framed  # t is a zero-framed [N, H+2, W+2, 8] image (input of a "fat pixel" first-layer conv)
 
@@ -95,7 +97,8 @@ class StandardizedC2d(nn.Conv2d):
         want_stats = want_stats and not nchw_out and os.environ.get("VQB_GN_STATS_FUSION", "1") == "1"
         kind = "fat3" if a.framed else self._kind()
         out = ops.conv(a.t, self.weight, self.bias, self._packed, kind,
-                       residual.t if residual is not None else None, relu, input_is_relu, nchw_out, want_stats)
+                       residual.t if residual is not None else None, relu, input_is_relu, nchw_out, want_stats,
+                       gn_link=a.link)
         if nchw_out:
             return out
         if want_stats:
@@ -119,15 +122,17 @@ class FP32GroupNorm(nn.GroupNorm):
 
     def forward(self, input, silu: bool = False):
         a, ext = _enter(input)
-        y = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu, chsums=a.stats)
-        return _exit(Act(y, a.C), ext)
+        link = ops.GnLink() if (silu and not ext) else None
+        y = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu, chsums=a.stats, link=link)
+        return _exit(Act(y, a.C, link=link), ext)
 
     def forward_with_skip(self, a: "Act", silu: bool = True):
         """-> (normalised activation, the input again). Consumers of the second output (the residual path) get their
         gradient summed inside the GroupNorm backward kernel (no separate accumulation pass)."""
+        link = ops.GnLink() if silu else None
         y, skip = ops.group_norm_silu(a.t, self.weight, self.bias, self.num_groups, self.eps, silu, with_skip=True,
-                                      chsums=a.stats)
-        return Act(y, a.C), Act(skip, a.C)
+                                      chsums=a.stats, link=link)
+        return Act(y, a.C, link=link), Act(skip, a.C)
 
 
 class AttnBlock(nn.Module):

@@ -61,7 +61,30 @@ struct alignas(64) ConvParams {
     const void* mask;
     const float* bias;
     float* stats;
+    // fused GroupNorm(+SiLU)-backward statistics (VQB_EPI_GNBWD, aux_tma == 3): this launch is the data gradient of the
+    // conv that consumed y = silu(GN(x)); its output IS dy of that GroupNorm, so the epilogue also reads the x tile
+    // (through xmap) and accumulates cs[n][c] = (sum_p du, sum_p du * xhat), du = dy * silu'(gamma*xhat + beta) — the
+    // whole "reduce" pass of the GroupNorm backward (x and dy read once more from HBM) disappears.
+    const float* gn_mr;     // [N][G][2] mean, rstd
+    const float* gn_gamma;  // [C]
+    const float* gn_beta;   // [C]
+    float* gn_cs;           // [N][C][2], pre-zeroed
+    int32_t gn_G, gn_lcpg;  // groups, log2(channels per group)
 };
+
+// One step of the transposing butterfly used by the fused GroupNorm-backward statistics: lanes whose bit OFF is set
+// keep the upper HALF of the (still 2*HALF) per-lane values, the others the lower, and each adds its partner's copy.
+template <int HALF, int OFF>
+__device__ __forceinline__ void bfly_step(float (&s1)[16], float (&s2)[16], uint32_t lane) {
+    const bool upper = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const float k1 = upper ? s1[i + HALF] : s1[i], t1 = upper ? s1[i] : s1[i + HALF];
+        const float k2 = upper ? s2[i + HALF] : s2[i], t2 = upper ? s2[i] : s2[i + HALF];
+        s1[i] = k1 + __shfl_xor_sync(0xffffffffu, t1, OFF);
+        s2[i] = k2 + __shfl_xor_sync(0xffffffffu, t2, OFF);
+    }
+}
 
 template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
@@ -628,6 +651,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         uint8_t* rowp = sbuf + r * 128u;
                         *reinterpret_cast<uint4*>(rowp + (((2 * c4) ^ (r & 7u)) << 4)) = o0;
                         *reinterpret_cast<uint4*>(rowp + (((2 * c4 + 1) ^ (r & 7u)) << 4)) = o1;
+                        if (p.aux_tma == 3) {
+                            // ---- GroupNorm-backward statistics of these 16 channels of this row (dy = the bf16 values
+                            // just staged, x = the TMA-prefetched tile of the GroupNorm's input)
+                            const uint8_t* arow = abuf + r * 128u;
+                            const uint4 x0 = *reinterpret_cast<const uint4*>(arow + (((2 * c4) ^ (r & 7u)) << 4));
+                            const uint4 x1 = *reinterpret_cast<const uint4*>(arow + (((2 * c4 + 1) ^ (r & 7u)) << 4));
+                            const uint32_t xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                            const uint32_t dd[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                            float s1[16], s2[16];
+                            const float* mrn = p.gn_mr + static_cast<int64_t>(on0) * p.gn_G * 2;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 xv = unpack_bf16x2(xx[j]);
+                                const float2 dv = unpack_bf16x2(dd[j]);
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const int c = col + 2 * j + h;
+                                    const int g = c >> p.gn_lcpg;
+                                    const float mean = live ? __ldg(mrn + 2 * g) : 0.f;
+                                    const float rstd = live ? __ldg(mrn + 2 * g + 1) : 0.f;
+                                    const float ga = live ? __ldg(p.gn_gamma + c) : 0.f;
+                                    const float be = live ? __ldg(p.gn_beta + c) : 0.f;
+                                    const float xh = ((h ? xv.y : xv.x) - mean) * rstd;
+                                    const float u = fmaf(xh, ga, be);
+                                    float sg;
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(sg) : "f"(0.5f * u));
+                                    sg = fmaf(0.5f, sg, 0.5f);
+                                    const float du = (h ? dv.y : dv.x) * (sg * (1.f + u * (1.f - sg)));
+                                    s1[2 * j + h] = live ? du : 0.f;
+                                    s2[2 * j + h] = live ? du * xh : 0.f;
+                                }
+                            }
+                            // transposing butterfly: 16 channels x 32 rows -> lane l ends with channel (l >> 1) & 15
+                            bfly_step<8, 16>(s1, s2, lane);
+                            bfly_step<4, 8>(s1, s2, lane);
+                            bfly_step<2, 4>(s1, s2, lane);
+                            bfly_step<1, 2>(s1, s2, lane);
+                            s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+                            s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+                            if ((lane & 1u) == 0)
+                                *reinterpret_cast<float2*>(sStat + (ew * 64 + c4 * 16 + ((lane >> 1) & 15u)) * 2) =
+                                    make_float2(s1[0], s2[0]);
+                        }
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(1, 128);
@@ -659,6 +725,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         if (col0 + c < p.Cout) {
                             const float v = sStat[t] + sStat[128 + t] + sStat[256 + t] + sStat[384 + t];
                             atomicAdd(p.stats + (static_cast<int64_t>(on0) * p.Cout + col0 + c) * 2 + (t & 1u), v);
+                        }
+                        named_bar_sync(2, 128);  // sStat is reused by the next group
+                    }
+                    if (p.aux_tma == 3) {
+                        named_bar_sync(2, 128);
+                        const uint32_t t = ew * 32 + lane;  // 0..127 -> (channel t/2, stat t&1)
+                        const int c = cg * 64 + static_cast<int>(t >> 1);
+                        if (col0 + c < p.Cout) {
+                            const float v = sStat[t] + sStat[128 + t] + sStat[256 + t] + sStat[384 + t];
+                            atomicAdd(p.gn_cs + (static_cast<int64_t>(on0) * p.Cout + col0 + c) * 2 + (t & 1u), v);
                         }
                         named_bar_sync(2, 128);  // sStat is reused by the next group
                     }
@@ -794,11 +870,29 @@ static int fill_views(const VqbView* views, int nviews, const void* a, int C, in
 using namespace vqb;
 
 static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias, const void* res,
-                          const void* mask, void* out, float* stats, void* stream, bool query_only);
+                          const void* mask, void* out, float* stats, void* stream, bool query_only,
+                          const VqbGnBwdFuse* gn = nullptr);
 
 extern "C" int vqb_conv_gemm(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias,
                              const void* res, const void* mask, void* out, float* stats, void* stream) {
     return conv_gemm_impl(d, a, w_packed, bias, res, mask, out, stats, stream, false);
+}
+
+// Data-gradient launch that also accumulates the statistics of the GroupNorm(+SiLU) backward whose dy it produces.
+extern "C" int vqb_conv_gemm_gnbwd(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias, void* out,
+                                   const VqbGnBwdFuse* gn, void* stream) {
+    VQB_CHECK(gn && gn->x && gn->mr && gn->gamma && gn->beta && gn->cs && gn->groups > 0,
+              "vqb_conv_gemm_gnbwd: incomplete VqbGnBwdFuse");
+    return conv_gemm_impl(d, a, w_packed, bias, nullptr, nullptr, out, nullptr, stream, false, gn);
+}
+
+// 1 if vqb_conv_gemm_gnbwd supports this descriptor with `groups` GroupNorm groups, else 0.
+extern "C" int vqb_conv_gnbwd_ok(const VqbConvDesc* d, int groups) {
+    if (!d || groups <= 0 || d->Cout % groups != 0) return 0;
+    const int cpg = d->Cout / groups;
+    if ((cpg & (cpg - 1)) != 0) return 0;
+    if (d->flags & (VQB_EPI_RES | VQB_EPI_MASK | VQB_EPI_STATS | VQB_EPI_RELU)) return 0;
+    return vqb_conv_stats_ok(d);  // same geometry conditions: staged epilogue, whole sub-tiles inside one image
 }
 
 // 1 if vqb_conv_gemm can produce GroupNorm statistics (VQB_EPI_STATS) for this descriptor, else 0.
@@ -813,7 +907,8 @@ extern "C" int vqb_conv_stats_ok(const VqbConvDesc* d) {
 }
 
 static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_packed, const float* bias, const void* res,
-                          const void* mask, void* out, float* stats, void* stream, bool query_only) {
+                          const void* mask, void* out, float* stats, void* stream, bool query_only,
+                          const VqbGnBwdFuse* gn) {
     VQB_CHECK(d && a && w_packed && out, "vqb_conv_gemm: null pointer");
     VQB_CHECK(d->C > 0 && d->C % 8 == 0, "vqb_conv_gemm: C=%d must be a positive multiple of 8", d->C);
     VQB_CHECK(d->Cout > 0 && d->N > 0 && d->H > 0 && d->W > 0, "vqb_conv_gemm: bad extents");
@@ -954,9 +1049,25 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     }
     p.do_stats = (d->flags & VQB_EPI_STATS) ? 1 : 0;
     if (query_only) return stats_ok ? 1 : 0;
+    p.gn_mr = p.gn_gamma = p.gn_beta = nullptr;
+    p.gn_cs = nullptr;
+    p.gn_G = p.gn_lcpg = 0;
+    if (gn) {
+        const int cpg = d->Cout / gn->groups;
+        VQB_CHECK(stats_ok && !(p_dbg & 512) && d->Cout % gn->groups == 0 && (cpg & (cpg - 1)) == 0 &&
+                      !(d->flags & (VQB_EPI_RES | VQB_EPI_MASK | VQB_EPI_STATS | VQB_EPI_RELU)),
+                  "vqb_conv_gemm_gnbwd: unsupported shape / flags (N=%d H=%d W=%d Cout=%d groups=%d)", d->N, d->H, d->W,
+                  d->Cout, gn->groups);
+        p.gn_mr = gn->mr;
+        p.gn_gamma = gn->gamma;
+        p.gn_beta = gn->beta;
+        p.gn_cs = gn->cs;
+        p.gn_G = gn->groups;
+        p.gn_lcpg = ilog2(static_cast<uint32_t>(cpg));
+    }
     const int stage_bytes = mtiles * kABytes + block_n * kBlockK * 2;
     // residual / ReLU-gate operand through TMA (debug bit 512 keeps the per-thread loads)
-    const int aux_tma = (tma_store && !(p_dbg & 512)) ? ((d->flags & VQB_EPI_RES) ? 1 : ((d->flags & VQB_EPI_MASK) ? 2 : 0)) : 0;
+    const int aux_tma = gn ? 3 : ((tma_store && !(p_dbg & 512)) ? ((d->flags & VQB_EPI_RES) ? 1 : ((d->flags & VQB_EPI_MASK) ? 2 : 0)) : 0);
     p.aux_tma = aux_tma;
     const int epi_smem = swap ? 4 * 16384 + 2048 : (tma_store ? 2 * 16384 + 2048 : 0) + (aux_tma ? 2 * 16384 : 0);
     p.epi_bytes = epi_smem;
@@ -1046,7 +1157,7 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
         rc = encode_tmap_bf16(&p.omap, out, 4, dims, str, box, 128);
         if (rc != VQB_OK) return rc;
         if (aux_tma) {
-            rc = encode_tmap_bf16(&p.xmap, aux_tma == 1 ? res : mask, 4, dims, str, box, 128);
+            rc = encode_tmap_bf16(&p.xmap, aux_tma == 1 ? res : (aux_tma == 2 ? mask : gn->x), 4, dims, str, box, 128);
             if (rc != VQB_OK) return rc;
         }
     }

@@ -812,21 +812,27 @@ int vqb_gn_silu_fwd_pre(const void* x, void* y, const float* gamma, const float*
 // GroupNorm(+SiLU) backward. ws: >= N*C*2 + N*G*2 floats. dx may alias dy. add (optional) is summed into dx.
 // dx_colsum (optional, [C] fp32, overwritten): per-channel sums of dx over all N*HW pixels, i.e. the bias gradient of the
 // convolution whose output this GroupNorm normalised, produced in the same pass instead of by vqb_colsum.
-int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
-                    const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
-                    float* dx_colsum, void* stream) {
+static int gn_silu_bwd_impl(const void* x, const void* dy, const void* add, void* dx, const float* gamma,
+                           const float* beta, const float* mr, const float* cs_pre, float* dgamma, float* dbeta, float* ws,
+                           int N, int HW, int C, int G, int silu, float* dx_colsum, void* stream) {
     VQB_CHECK(x && dy && dx && gamma && beta && mr && dgamma && dbeta && ws, "vqb_gn_silu_bwd: null pointer");
     VQB_CHECK(C % 8 == 0 && C % G == 0 && C <= 2048, "vqb_gn_silu_bwd: C=%d G=%d unsupported", C, G);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float* cs = ws;
-    float* gsum = ws + static_cast<int64_t>(N) * C * 2;
-    VQB_CUDA(cudaMemsetAsync(cs, 0, sizeof(float) * 2 * N * C, st));
     int chunks, ppc;
     const int T = cv_threads(C);
-    cv_grid(HW, C, N, gn_bwd_reduce_kernel, 2 * C * sizeof(float), chunks, ppc);
-    gn_bwd_reduce_kernel<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mr, gamma, beta, cs, HW, C, G,
-        ppc, silu);
+    const float* cs = cs_pre;
+    float* gsum = ws;
+    if (!cs_pre) {  // statistics pass (skipped when the consumer conv's data-gradient epilogue produced them)
+        float* csw = ws;
+        gsum = ws + static_cast<int64_t>(N) * C * 2;
+        VQB_CUDA(cudaMemsetAsync(csw, 0, sizeof(float) * 2 * N * C, st));
+        cv_grid(HW, C, N, gn_bwd_reduce_kernel, 2 * C * sizeof(float), chunks, ppc);
+        gn_bwd_reduce_kernel<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mr, gamma, beta, csw, HW, C,
+            G, ppc, silu);
+        cs = csw;
+        count_launch();
+    }
     const int fin = (N * G > C ? N * G : C);
     gn_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(cs, gamma, gsum, dgamma, dbeta, N, C, G, HW);
     const size_t cs_smem = dx_colsum ? C * sizeof(float) : 0;
@@ -844,8 +850,22 @@ int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, co
             static_cast<__nv_bfloat16*>(dx), mr, gsum, gamma, beta, HW, C, G, ppc, silu, dx_colsum);
     }
     VQB_CUDA(cudaGetLastError());
-    count_launch(3);
+    count_launch(2);
     return VQB_OK;
+}
+
+int vqb_gn_silu_bwd(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
+                    const float* mr, float* dgamma, float* dbeta, float* ws, int N, int HW, int C, int G, int silu,
+                    float* dx_colsum, void* stream) {
+    return gn_silu_bwd_impl(x, dy, add, dx, gamma, beta, mr, nullptr, dgamma, dbeta, ws, N, HW, C, G, silu, dx_colsum,
+                            stream);
+}
+
+int vqb_gn_silu_bwd_pre(const void* x, const void* dy, const void* add, void* dx, const float* gamma, const float* beta,
+                        const float* mr, const float* cs, float* dgamma, float* dbeta, float* ws, int N, int HW, int C,
+                        int G, int silu, float* dx_colsum, void* stream) {
+    VQB_CHECK(cs, "vqb_gn_silu_bwd_pre: null cs");
+    return gn_silu_bwd_impl(x, dy, add, dx, gamma, beta, mr, cs, dgamma, dbeta, ws, N, HW, C, G, silu, dx_colsum, stream);
 }
 
 int vqb_wavelet_fwd(const float* x, void* y, const float* filt, int N, int C, int H, int W, int Cpad, void* stream) {
