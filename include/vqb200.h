@@ -267,6 +267,12 @@ typedef struct VqbAdamwGroup {
 } VqbAdamwGroup;
 int vqb_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* chunk_group,
                    int64_t nchunks, int ngroups, const VqbAdamwGroup* groups_host, float grad_scale, void* stream);
+/* CUDA-graph friendly form: the per-group hyper-parameters (incl. bias corrections) are read from a 28-float DEVICE
+ * record at kernel run time. vqb_adamw_fill_record (host function) builds that record from groups_host into host memory;
+ * the caller copies it to record_dev on the launch stream before every launch / graph replay. */
+int vqb_adamw_fill_record(int ngroups, const VqbAdamwGroup* groups_host, float* record_host);
+int vqb_adamw_flat_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* chunk_group,
+                       int64_t nchunks, const float* record_dev, float grad_scale, void* stream);
 
 /*
  * Re-pack every cached bf16 GEMM operand of the fp32 OIHW master weights in one launch (after an optimizer step).

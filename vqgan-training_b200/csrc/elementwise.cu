@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace vqb {
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
@@ -463,6 +465,257 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     }
 }
 
+
+// ------------------------------------------------------------------ GroupNorm backward, persistent L2-pipelined form
+// One persistent launch does reduce AND apply. The two-kernel form reads x and dy twice from HBM (10 B/element, 12 with
+// the skip gradient). Here the work is ordered  R(0) R(1) A(0) R(2) A(1) ... A(N-1)  (R(n) = statistics of sample n,
+// A(n) = dx of sample n): when A(n) re-reads x, dy of sample n they were streamed at most one sample ago and (for every
+// layer of the FLUX config: x + dy of one sample <= 34 MB of the 126 MB L2) are still L2 resident — HBM traffic drops to
+// read-once + write-once = 6 (8) B/element. R loads carry an L2 evict_last policy, A loads / dx stores evict_first.
+// Sync: R units add their per-channel partials to cs[n] (fp32 atomics) and bump done[n]; A units spin (acquire) until
+// done[n] == units. Every CTA walks the same global order and only ever waits on work that precedes its own position in
+// every CTA's list, and the grid is sized to be fully co-resident, so the wait cannot deadlock.
+//
+// Per element (trimmed: the reduce kernel sat on the FP32-issue / SFU limit):  h = x*a2 + b2 (= u/2), t = tanh(h),
+// 2*silu'(u) = (1 + t) * (1 + h - h*t);  du2 = dy * that;  S_du = sum du2 / 2,  S_duxh = rstd/2 * sum du2*(x - mean);
+// dx = du2*(gamma*rstd/2) - rstd*gS1 - (x - mean)*rstd^2*gS2 (+ add).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg16_hint(const __nv_bfloat16* ptr, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg16_hint(__nv_bfloat16* ptr, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
+
+template <bool ADD, bool SILU>
+__global__ void __launch_bounds__(256, 2)
+gn_bwd_persistent_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                         const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
+                         const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* cs /* [N][C][2], zeroed */, int* done /* [N], zeroed */, float* __restrict__ colsum,
+                         int N, int HW, int C, int G, int units, int pix_per_unit) {
+    extern __shared__ float sm[];  // [2C] partial sums | [C] dx column sums (A phase) ; then [2G] group sums
+    float* sm_gs = sm + 2 * C;
+    const int V = C >> 3, R = blockDim.x / V;
+    const int cv = threadIdx.x % V, pr = threadIdx.x / V;
+    const int cpg = C / G;
+    const bool worker = pr < R;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+    float ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        ga[j] = gamma[cv * 8 + j];
+        be[j] = beta[cv * 8 + j];
+    }
+    float csum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[j] = 0.f;
+
+    for (int step = 0; step <= N; ++step) {
+        // ---------------------------------------------------------------- R(step)
+        if (step < N) {
+            const int n = step;
+            float mean[8], a2[8], b2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int g = (cv * 8 + j) / cpg;
+                mean[j] = mr[(n * G + g) * 2];
+                const float a = ga[j] * mr[(n * G + g) * 2 + 1];
+                a2[j] = 0.5f * a;
+                b2[j] = 0.5f * (be[j] - mean[j] * a);
+            }
+            const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+                __syncthreads();
+                if (worker) {
+                    float s1[8], s2[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+                    const int p0 = u * pix_per_unit, p1 = min(HW, p0 + pix_per_unit);
+                    for (int p = p0 + pr; p < p1; p += 4 * R) {
+                        uint4 ux[4], ud[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const bool in = (p + k * R) < p1;
+                            ux[k] = in ? ldg16_hint(x + base + static_cast<int64_t>(p + k * R) * C, pol_keep)
+                                       : make_uint4(0, 0, 0, 0);
+                            ud[k] = in ? ldg16_hint(dy + base + static_cast<int64_t>(p + k * R) * C, pol_keep)
+                                       : make_uint4(0, 0, 0, 0);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if ((p + k * R) >= p1) break;
+                            float f[8], d[8];
+                            cvt8(ux[k], f);
+                            cvt8(ud[k], d);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float du2 = 2.f * d[j];
+                                if (SILU) {
+                                    const float h = fmaf(f[j], a2[j], b2[j]);
+                                    const float t = tanh_approx(h);
+                                    const float r = fmaf(-h, t, h + 1.f);
+                                    du2 = d[j] * fmaf(t, r, r);
+                                }
+                                s1[j] += du2;
+                                s2[j] = fmaf(du2, f[j] - mean[j], s2[j]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        atomicAdd(&sm[(cv * 8 + j) * 2], s1[j]);
+                        atomicAdd(&sm[(cv * 8 + j) * 2 + 1], s2[j]);
+                    }
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+                    const int g = (i >> 1) / cpg;
+                    const float rstd = mr[(n * G + g) * 2 + 1];
+                    // cs[n][c] = (sum du, sum du*xhat)
+                    atomicAdd(&cs[static_cast<int64_t>(n) * 2 * C + i], sm[i] * ((i & 1) ? 0.5f * rstd : 0.5f));
+                }
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) atomicAdd(&done[n], 1);
+            }
+        }
+        // ---------------------------------------------------------------- A(step - 1)
+        if (step >= 1) {
+            const int n = step - 1;
+            bool mine = false;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) mine = true;
+            if (mine) {
+                if (threadIdx.x == 0) {
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + n) : "memory");
+                    } while (v < units);
+                }
+                __syncthreads();
+                // group sums gs[g] = (sum_c gamma_c cs0, sum_c gamma_c cs1) / m from the now complete cs[n]
+                for (int g = threadIdx.x; g < G; g += blockDim.x) {
+                    float a = 0.f, b = 0.f;
+                    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                        a = fmaf(gamma[c], __ldcg(&cs[(static_cast<int64_t>(n) * C + c) * 2]), a);
+                        b = fmaf(gamma[c], __ldcg(&cs[(static_cast<int64_t>(n) * C + c) * 2 + 1]), b);
+                    }
+                    const float m = static_cast<float>(cpg) * HW;
+                    sm_gs[g * 2] = a / m;
+                    sm_gs[g * 2 + 1] = b / m;
+                }
+                __syncthreads();
+                float mean[8], a2[8], b2[8], k0[8], k1[8], k2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = (cv * 8 + j) / cpg;
+                    mean[j] = mr[(n * G + g) * 2];
+                    const float rstd = mr[(n * G + g) * 2 + 1];
+                    const float a = ga[j] * rstd;
+                    a2[j] = 0.5f * a;
+                    b2[j] = 0.5f * (be[j] - mean[j] * a);
+                    k1[j] = 0.5f * a;                        // du2 * k1 = du * gamma * rstd
+                    k0[j] = -rstd * sm_gs[g * 2];
+                    k2[j] = -rstd * rstd * sm_gs[g * 2 + 1];
+                }
+                const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+                if (worker) {
+                    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                        const int p0 = u * pix_per_unit, p1 = min(HW, p0 + pix_per_unit);
+                        constexpr int U = ADD ? 2 : 3;
+                        for (int pp = p0 + pr; pp < p1; pp += U * R) {
+                            uint4 ux[U], ud[U], ua[U];
+#pragma unroll
+                            for (int k = 0; k < U; ++k) {
+                                const bool in = (pp + k * R) < p1;
+                                const int64_t off = base + static_cast<int64_t>(pp + k * R) * C;
+                                ux[k] = in ? ldg16_hint(x + off, pol_drop) : make_uint4(0, 0, 0, 0);
+                                ud[k] = in ? ldg16_hint(dy + off, pol_drop) : make_uint4(0, 0, 0, 0);
+                                if (ADD) ua[k] = in ? ldg16_hint(add + off, pol_drop) : make_uint4(0, 0, 0, 0);
+                            }
+#pragma unroll
+                            for (int k = 0; k < U; ++k) {
+                                if ((pp + k * R) >= p1) break;
+                                float f[8], d[8], r8[8];
+                                cvt8(ux[k], f);
+                                cvt8(ud[k], d);
+                                if (ADD) cvt8(ua[k], r8);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float du2 = 2.f * d[j];
+                                    if (SILU) {
+                                        const float h = fmaf(f[j], a2[j], b2[j]);
+                                        const float t = tanh_approx(h);
+                                        const float r = fmaf(-h, t, h + 1.f);
+                                        du2 = d[j] * fmaf(t, r, r);
+                                    }
+                                    float v = fmaf(du2, k1[j], fmaf(f[j] - mean[j], k2[j], k0[j]));
+                                    if (ADD) v += r8[j];
+                                    f[j] = v;
+                                    csum[j] += __bfloat162float(__float2bfloat16(v));
+                                }
+                                uint4 o;
+                                o.x = pack_bf16x2(f[0], f[1]);
+                                o.y = pack_bf16x2(f[2], f[3]);
+                                o.z = pack_bf16x2(f[4], f[5]);
+                                o.w = pack_bf16x2(f[6], f[7]);
+                                stg16_hint(dx + base + static_cast<int64_t>(pp + k * R) * C, o, pol_drop);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();  // sm_gs is rewritten by the next sample
+            }
+        }
+    }
+    // dx column sums (= bias gradient of the conv that produced x): once per CTA
+    if (colsum) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+        if (worker) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], csum[j]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], sm[i]);
+    }
+}
+
+// dgamma[c] = sum_n cs[n][c][1], dbeta[c] = sum_n cs[n][c][0]
+__global__ void gn_bwd_param_grads_kernel(const float* __restrict__ cs, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta, int N, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C) return;
+    float a = 0.f, b = 0.f;
+    for (int n = 0; n < N; ++n) {
+        a += cs[(static_cast<int64_t>(n) * C + i) * 2];
+        b += cs[(static_cast<int64_t>(n) * C + i) * 2 + 1];
+    }
+    dbeta[i] = a;
+    dgamma[i] = b;
+}
+
 // ------------------------------------------------------------------ nearest 2x up-sampling
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                   int W, int C) {
@@ -822,6 +1075,49 @@ static int gn_silu_bwd_impl(const void* x, const void* dy, const void* add, void
     const int T = cv_threads(C);
     const float* cs = cs_pre;
     float* gsum = ws;
+    // Persistent L2-pipelined form (reduce + apply in one launch, x / dy read from HBM once): used when one sample's
+    // x + dy (+ add) comfortably fits the L2 next to the following sample's, and there is enough work to pipeline.
+    static const bool persistent_on = [] {
+        const char* e = getenv("VQB_GN_BWD_PERSISTENT");
+        return !(e && e[0] == '0');
+    }();
+    const int64_t sample_bytes = static_cast<int64_t>(HW) * C * 2 * (add ? 3 : 2);
+    if (!cs_pre && persistent_on && T <= 256 && sample_bytes <= (40ll << 20) && N >= 2 &&
+        static_cast<int64_t>(HW) * C >= (1 << 16)) {
+        const int V = C / 8, R = T / V;
+        float* csw = ws;                                                   // [N][C][2]
+        int* done = reinterpret_cast<int*>(ws + static_cast<int64_t>(N) * C * 2);  // [N] (<= N*G*2 floats of ws)
+        VQB_CUDA(cudaMemsetAsync(csw, 0, sizeof(float) * (2 * N * C + N), st));
+        if (dx_colsum) VQB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
+        const size_t smem = (2 * C + 2 * G) * sizeof(float);
+        auto launch = [&](auto kern) -> int {
+            int bpsm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, T, smem) != cudaSuccess || bpsm < 1)
+                return set_error(VQB_ECUDA, "vqb_gn_silu_bwd: occupancy query failed");
+            if (bpsm > 2) bpsm = 2;
+            const int grid = (num_sms() > 0 ? num_sms() : 148) * bpsm;
+            int units = grid;  // one R unit and one A unit per CTA and sample when the sample is large enough
+            const int min_ppu = R * 4;
+            if (HW / units < min_ppu) units = HW / min_ppu > 0 ? HW / min_ppu : 1;
+            int ppu = (HW + units - 1) / units;
+            ppu = ((ppu + R - 1) / R) * R;
+            units = (HW + ppu - 1) / ppu;
+            kern<<<grid, T, smem, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
+                                        static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), mr,
+                                        gamma, beta, csw, done, dx_colsum, N, HW, C, G, units, ppu);
+            return VQB_OK;
+        };
+        int rc;
+        if (add)
+            rc = silu ? launch(gn_bwd_persistent_kernel<true, true>) : launch(gn_bwd_persistent_kernel<true, false>);
+        else
+            rc = silu ? launch(gn_bwd_persistent_kernel<false, true>) : launch(gn_bwd_persistent_kernel<false, false>);
+        if (rc != VQB_OK) return rc;
+        gn_bwd_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(csw, dgamma, dbeta, N, C);
+        VQB_CUDA(cudaGetLastError());
+        count_launch(2);
+        return VQB_OK;
+    }
     if (!cs_pre) {  // statistics pass (skipped when the consumer conv's data-gradient epilogue produced them)
         float* csw = ws;
         gsum = ws + static_cast<int64_t>(N) * C * 2;

@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstring>
+
 namespace vqb {
 
 // ------------------------------------------------------------------ AdamW (decoupled weight decay; torch.optim.AdamW
@@ -22,10 +24,14 @@ struct AdamwGroups {
         eps[VQB_ADAMW_MAX_GROUPS], wd[VQB_ADAMW_MAX_GROUPS], bc1[VQB_ADAMW_MAX_GROUPS], bc2_sqrt[VQB_ADAMW_MAX_GROUPS];
 };
 
+// hyper-parameters either by value (h) or, hdev != nullptr, from DEVICE memory (one AdamwGroups record the host refreshes
+// before every launch / CUDA-graph replay: learning-rate schedules and bias corrections then need no re-capture)
 __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v,
                                                          const uint8_t* __restrict__ chunk_group, int64_t nchunks,
-                                                         AdamwGroups h, float grad_scale) {
+                                                         AdamwGroups h, const AdamwGroups* __restrict__ hdev,
+                                                         float grad_scale) {
+    if (hdev) h = *hdev;
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const int grp = chunk_group[c];
         if (grp >= VQB_ADAMW_MAX_GROUPS) continue;
@@ -134,7 +140,44 @@ int vqb_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp
     const int64_t cap = static_cast<int64_t>(num_sms() > 0 ? num_sms() : 148) * 16;
     if (blocks > cap) blocks = cap;
     adamw_flat_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        params, grads, exp_avg, exp_avg_sq, chunk_group, nchunks, h, grad_scale);
+        params, grads, exp_avg, exp_avg_sq, chunk_group, nchunks, h, nullptr, grad_scale);
+    VQB_CUDA(cudaGetLastError());
+    count_launch();
+    return VQB_OK;
+}
+
+// Fills the 28-float device record of vqb_adamw_flat_dev from host-side group descriptions (host function: the caller
+// copies `record_host` to the device, e.g. from pinned memory on the launch stream).
+int vqb_adamw_fill_record(int ngroups, const VqbAdamwGroup* groups_host, float* record_host /* [28] */) {
+    VQB_CHECK(groups_host && record_host && ngroups >= 1 && ngroups <= VQB_ADAMW_MAX_GROUPS,
+              "vqb_adamw_fill_record: bad arguments");
+    AdamwGroups h;
+    for (int i = 0; i < VQB_ADAMW_MAX_GROUPS; ++i) {
+        const VqbAdamwGroup& s = groups_host[i < ngroups ? i : 0];
+        VQB_CHECK(s.step >= 1, "vqb_adamw_fill_record: step must be >= 1");
+        h.lr[i] = s.lr; h.beta1[i] = s.beta1; h.beta2[i] = s.beta2; h.eps[i] = s.eps; h.wd[i] = s.weight_decay;
+        h.bc1[i] = static_cast<float>(1.0 - pow(static_cast<double>(s.beta1), static_cast<double>(s.step)));
+        h.bc2_sqrt[i] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(s.beta2), static_cast<double>(s.step))));
+    }
+    static_assert(sizeof(AdamwGroups) == 28 * sizeof(float), "record layout");
+    memcpy(record_host, &h, sizeof(h));
+    return VQB_OK;
+}
+
+int vqb_adamw_flat_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* chunk_group,
+                       int64_t nchunks, const float* record_dev, float grad_scale, void* stream) {
+    VQB_CHECK(params && grads && exp_avg && exp_avg_sq && chunk_group && record_dev, "vqb_adamw_flat_dev: null pointer");
+    VQB_CHECK((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) % 16 == 0,
+              "vqb_adamw_flat_dev: buffers must be 16-byte aligned");
+    if (nchunks <= 0) return VQB_OK;
+    int64_t blocks = nchunks;
+    const int64_t cap = static_cast<int64_t>(num_sms() > 0 ? num_sms() : 148) * 16;
+    if (blocks > cap) blocks = cap;
+    AdamwGroups dummy = {};
+    adamw_flat_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        params, grads, exp_avg, exp_avg_sq, chunk_group, nchunks, dummy,
+        reinterpret_cast<const AdamwGroups*>(record_dev), grad_scale);
     VQB_CUDA(cudaGetLastError());
     count_launch();
     return VQB_OK;

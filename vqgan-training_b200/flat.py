@@ -124,6 +124,7 @@ class FlatAdamW(torch.optim.Optimizer):
                              "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view(p.shape)}
         self._chunk_tables = {}
         self.grad_scale = 1.0
+        self._rec_dev = None
 
     def _chunk_table(self, active):
         t = self._chunk_tables.get(active)
@@ -143,6 +144,44 @@ class FlatAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         self.store.zero_grad()
 
+    # The step is split so that a captured CUDA graph can contain the kernel while the host still drives the schedule:
+    #   upload_hyper()  host: advance the step counts, compute lr / bias corrections, copy the 28-float record to the
+    #                   device (pinned ring buffer, stream-ordered) — runs BEFORE a graph replay
+    #   launch()        device: vqb_adamw_flat_dev (+ the re-pack of the bf16 operands when pack=True) — capturable
+    def upload_hyper(self, active=None):
+        if self._rec_dev is None:
+            dev = self.store.params.device
+            self._rec_dev = torch.zeros(28, device=dev, dtype=torch.float32)
+            self._rec_pin = [torch.zeros(28, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._rec_ev = [None] * 4
+            self._rec_i = 0
+        groups = (native.VqbAdamwGroup * len(self.param_groups))()
+        for gi, g in enumerate(self.param_groups):
+            if active is None or any(active[i] for i in range(len(active)) if self._group_of[i] == gi):
+                g["step"] += 1
+            b1, b2 = g["betas"]
+            groups[gi] = native.VqbAdamwGroup(lr=float(g["lr"]), beta1=float(b1), beta2=float(b2), eps=float(g["eps"]),
+                                              weight_decay=float(g["weight_decay"]), step=max(1, int(g["step"])))
+        i = self._rec_i
+        self._rec_i = (i + 1) % len(self._rec_pin)
+        if self._rec_ev[i] is not None:
+            self._rec_ev[i].synchronize()  # the copy that last read this pinned slot (4 steps ago) has executed
+        native.check(native.load().vqb_adamw_fill_record(len(self.param_groups), groups, self._rec_pin[i].data_ptr()),
+                     "adamw_fill_record")
+        self._rec_dev.copy_(self._rec_pin[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._rec_ev[i] = ev
+
+    def launch(self, active, pack=False):
+        tab = self._chunk_table(active)
+        native.check(native.load().vqb_adamw_flat_dev(
+            self.store.params.data_ptr(), self.store.grads.data_ptr(), self.exp_avg.data_ptr(),
+            self.exp_avg_sq.data_ptr(), tab.data_ptr(), self.store.total // CHUNK, self._rec_dev.data_ptr(),
+            C.c_float(self.grad_scale), native.stream_ptr()), "adamw_flat_dev")
+        if pack:
+            ops.weights_updated(self.store.plist)
+
     @torch.no_grad()
     def step(self, closure=None):
         if not self.store.params.is_cuda:
@@ -150,17 +189,7 @@ class FlatAdamW(torch.optim.Optimizer):
         active = self.store.collect()
         if not any(active):
             return None
-        groups = (native.VqbAdamwGroup * len(self.param_groups))()
-        for gi, g in enumerate(self.param_groups):
-            if any(active[i] for i in range(len(active)) if self._group_of[i] == gi):
-                g["step"] += 1
-            b1, b2 = g["betas"]
-            groups[gi] = native.VqbAdamwGroup(lr=float(g["lr"]), beta1=float(b1), beta2=float(b2), eps=float(g["eps"]),
-                                              weight_decay=float(g["weight_decay"]), step=max(1, int(g["step"])))
-        tab = self._chunk_table(active)
-        native.check(native.load().vqb_adamw_flat(
-            self.store.params.data_ptr(), self.store.grads.data_ptr(), self.exp_avg.data_ptr(),
-            self.exp_avg_sq.data_ptr(), tab.data_ptr(), self.store.total // CHUNK, len(self.param_groups), groups,
-            C.c_float(self.grad_scale), native.stream_ptr()), "adamw_flat")
+        self.upload_hyper(active)
+        self.launch(active)
         # the global optimizer post-step hook (ops._optimizer_post_step) re-packs the bf16 operands of these weights
         return None

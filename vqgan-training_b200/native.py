@@ -119,6 +119,8 @@ def load():
         "vqb_wgrad_reduce_fold": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
         "vqb_adamw_flat": (i32, [vp, vp, vp, vp, vp, i64, i32, C.POINTER(VqbAdamwGroup), f32, vp]),
         "vqb_pack_weights_multi": (i32, [vp, i32, i32, vp]),
+        "vqb_adamw_fill_record": (i32, [i32, C.POINTER(VqbAdamwGroup), vp]),
+        "vqb_adamw_flat_dev": (i32, [vp, vp, vp, vp, vp, i64, vp, f32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name, None)

@@ -282,7 +282,11 @@ class GnLink:
         self.groups, self.silu, self.sums = 0, False, None
 
 
-_GN_BWD_FUSE = os.environ.get("VQB_GN_BWD_FUSE", "1") == "1"
+# Opt-in (VQB_GN_BWD_FUSE=1): measured on the B=32 step, the extra ~1200 instructions per 64-channel group in the four
+# epilogue warps are NOT hidden behind the main loop of the 128-channel layers (conv_gemm total 46.1 -> 64.9 ms for a
+# 5.2 ms saving in gn_bwd_reduce); kept, with its parity test, for layers with long K loops.
+_GN_BWD_FUSE = os.environ.get("VQB_GN_BWD_FUSE", "0") == "1"
+_GN_BWD_FUSE_MIN_C = int(os.environ.get("VQB_GN_BWD_FUSE_MIN_C", "0"))
 
 
 def conv_gnbwd_supported(g: plans.ConvGeom, Cout: int, out_strides, groups: int) -> bool:
@@ -617,7 +621,8 @@ class ConvFn(torch.autograd.Function):
                 wpd = cache.get(weight, ("dgrad", kind), gd.tapmap, True, Cop)
                 link = ctx.gn_link
                 ostr = plans.nhwc_strides(H, W, Cp)
-                if (link is not None and mask is None and Cp == Cin and link.silu and link.x is not None
+                if (link is not None and mask is None and Cp == Cin and Cin >= _GN_BWD_FUSE_MIN_C and link.silu
+                        and link.x is not None
                         and link.x.shape == gx.shape and conv_gnbwd_supported(gd, Cin, ostr, link.groups)):
                     # this data gradient IS the dy of the GroupNorm(+swish) that produced x: its epilogue also
                     # accumulates that GroupNorm's backward statistics (the separate reduction pass disappears)

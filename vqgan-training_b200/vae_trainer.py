@@ -57,20 +57,23 @@ class GradNormFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight):
-        ctx.save_for_backward(weight)
+        # `weight` may be a python number (what gradnorm() passes: no host->device tensor creation inside the step, which
+        # keeps the step CUDA-graph capturable) or a 0-dim tensor (the reference's calling convention, :51-53)
+        ctx.weight = weight
         return x.clone()
 
     @staticmethod
     def backward(ctx, grad_output):
-        weight = ctx.saved_tensors[0]
+        weight = ctx.weight
         n = torch.linalg.vector_norm(grad_output.float())
         if _dist_on():
             dist.all_reduce(n, op=dist.ReduceOp.AVG)
-        return (weight.to(grad_output.dtype) / (n + 1e-8).to(grad_output.dtype)) * grad_output, None
+        if torch.is_tensor(weight):
+            weight = weight.to(device=grad_output.device, dtype=grad_output.dtype)
+        return (weight / (n + 1e-8).to(grad_output.dtype)) * grad_output, None
 
 
 def gradnorm(x, weight=1.0):
-    weight = torch.tensor(weight, device=x.device)
     return GradNormFunction.apply(x, weight)
 
 
@@ -385,8 +388,17 @@ class Trainer:
                  use_wavelet=False, do_ganloss=False, learning_rate_vae=1e-5, learning_rate_disc=2e-4, max_steps=1000,
                  do_clamp=False, clamp_th=8.0, crop_invariance=False, flip_invariance=False,
                  augment_before_perceptual_loss=False, downscale_factor=16, use_lecam=False, disc_type="bce",
-                 lpips_eval=True, seed=42, use_vq=False, vq_codebook_size=8192, vq_beta=0.25):
+                 lpips_eval=True, seed=42, use_vq=False, vq_codebook_size=8192, vq_beta=0.25, cuda_graph=None):
         self.device = device
+        # CUDA-graph the whole step (forward, backward, NCCL collectives, optimizers, weight re-pack): ~600-1100 launches
+        # per step otherwise keep the host within ~10 % of being the limiter. Auto-enabled (None) when no host-side
+        # random branch changes the graph from step to step; VQB_CUDA_GRAPH=0 disables.
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("VQB_CUDA_GRAPH", "1") == "1"
+        self._graph_wanted = bool(cuda_graph) and not (crop_invariance or flip_invariance or
+                                                       augment_before_perceptual_loss)
+        self._graph = None          # (key, CUDAGraph, static input, static outputs, launches per step)
+        self._graph_warm = 0
         self.do_ganloss, self.do_clamp, self.clamp_th = do_ganloss, do_clamp, clamp_th
         self.crop_invariance, self.flip_invariance = crop_invariance, flip_invariance
         self.augment_before_perceptual_loss = augment_before_perceptual_loss
@@ -442,17 +454,75 @@ class Trainer:
         self.global_step = 0
         self.last = {}
 
+    GRAPH_WARMUP_STEPS = 3
+
     def step(self, real_images_hr: torch.Tensor):
+        """One iteration of vae_trainer.py:530-708. Host-side random decisions (the horizontal flip of :534-536 and the
+        draws of the equivariance augmentations) are taken here, in the reference's order; the device work runs either
+        eagerly or — after GRAPH_WARMUP_STEPS eager steps — as one CUDA-graph replay."""
+        flip = random.random() < 0.5  # :534-536
+        key = (tuple(real_images_hr.shape), real_images_hr.dtype)
+        use_graph = self._graph_wanted and real_images_hr.dtype == torch.float32 and \
+            (self._graph is None or self._graph[0] == key)
+        if not use_graph or self._graph_warm < self.GRAPH_WARMUP_STEPS:
+            self._graph_warm += 1
+            x = real_images_hr.to(self.device, non_blocking=True)
+            if flip:
+                x = torch.flip(x, [-1])
+            out = self._step_body(x, graph_mode=False)
+        else:
+            out = self._step_graph(real_images_hr, flip, key)
+            for _ in range(3):
+                random.random()  # the three draws of latent_augment (:567,572,577), which the replay does not execute
+        self.lr_scheduler.step()
+        self.global_step += 1
+        self.last = out
+        return out
+
+    def _step_graph(self, real_images_hr, flip, key):
+        if self._graph is None:
+            static_in = torch.empty(key[0], device=self.device, dtype=torch.float32)
+            static_in.copy_(real_images_hr, non_blocking=True)
+            import native
+
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            st_state = random.getstate()
+            l0 = native.launch_count()
+            with torch.cuda.graph(g):
+                out = self._step_body(static_in, graph_mode=True)
+            random.setstate(st_state)  # the capture ran the python body once: its draws are re-done by step()
+            self._graph = (key, g, static_in, out, native.launch_count() - l0)
+        _, g, static_in, out, _ = self._graph
+        if flip:
+            static_in.copy_(torch.flip(real_images_hr.to(self.device, non_blocking=True), [-1]))
+        else:
+            static_in.copy_(real_images_hr, non_blocking=True)
+        self.optimizer_G.upload_hyper()
+        if self.do_ganloss:
+            self.optimizer_D.upload_hyper()
+        g.replay()
+        return out
+
+    @property
+    def graph_launches_per_step(self):
+        """Kernels of libvqb200.so inside one replay of the captured step (None while running eagerly)."""
+        return self._graph[4] if self._graph is not None else None
+
+    def _opt_step(self, opt, graph_mode):
+        if graph_mode:  # capturable form: the hyper-parameter record is uploaded by _step_graph before every replay
+            active = opt.store.collect()
+            opt.launch(active, pack=True)
+        else:
+            opt.step()
+
+    def _step_body(self, real_images_hr: torch.Tensor, graph_mode: bool):
         vae, disc = self.vae, self.discriminator
         device = self.device
-        real_images_hr = real_images_hr.to(device, non_blocking=True)
         if real_images_hr.shape[-2:] != (256, 256):
             real_images_for_enc = F.interpolate(real_images_hr, size=(256, 256), mode="area")  # :531-533
         else:
             real_images_for_enc = real_images_hr  # the area resize is an exact identity at 256^2
-        if random.random() < 0.5:  # :534-536
-            real_images_for_enc = torch.flip(real_images_for_enc, [-1])
-            real_images_hr = torch.flip(real_images_hr, [-1])
 
         z = vae.module.encoder(real_images_for_enc)  # :538
         z_for_stats = z.detach()
@@ -477,10 +547,9 @@ class Trainer:
             d_loss, avg_real_logits, avg_fake_logits, disc_acc = gan_disc_loss(real_preds, fake_preds, self.disc_type)
             avg_real_logits = avg_scalar_over_nodes(avg_real_logits, device)
             avg_fake_logits = avg_scalar_over_nodes(avg_fake_logits, device)
-            self.lecam_anchor_real_logits = self.lecam_beta * self.lecam_anchor_real_logits + \
-                (1 - self.lecam_beta) * avg_real_logits
-            self.lecam_anchor_fake_logits = self.lecam_beta * self.lecam_anchor_fake_logits + \
-                (1 - self.lecam_beta) * avg_fake_logits
+            # in place: the anchors are persistent device scalars (also across CUDA-graph replays)
+            self.lecam_anchor_real_logits.mul_(self.lecam_beta).add_(avg_real_logits, alpha=1 - self.lecam_beta)
+            self.lecam_anchor_fake_logits.mul_(self.lecam_beta).add_(avg_fake_logits, alpha=1 - self.lecam_beta)
             total_d_loss = d_loss.mean()
             out["d_loss"] = total_d_loss.detach()
             lecam_loss_item = torch.zeros((), device=device)
@@ -492,7 +561,7 @@ class Trainer:
             self.optimizer_D.zero_grad(set_to_none=True)
             total_d_loss.backward()
             disc.allreduce_grads()
-            self.optimizer_D.step()
+            self._opt_step(self.optimizer_D, graph_mode)
             out.update(avg_real_logits=avg_real_logits, avg_fake_logits=avg_fake_logits, disc_acc=disc_acc,
                        lecam_loss=lecam_loss_item)
 
@@ -530,13 +599,10 @@ class Trainer:
 
         overall_vae_loss.backward()  # :701
         vae.allreduce_grads()        # the all-reduce the reference intends
-        self.optimizer_G.step()
+        self._opt_step(self.optimizer_G, graph_mode)
         self.optimizer_G.zero_grad(set_to_none=True)
-        self.lr_scheduler.step()
-        self.global_step += 1
         out.update(overall_vae_loss=overall_vae_loss.detach(), perceptual_loss=percep_rec_loss.detach(),
                    loss_data=loss_data, z=z_for_stats, reconstructed=reconstructed.detach())
-        self.last = out
         return out
 
     @torch.no_grad()
