@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--gan", action="store_true", help="alias of --config gan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-B200 peer leg")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA-graph replay")
     args = ap.parse_args()
     if args.gan and args.config == "lpips":
         args.config = "gan"
@@ -448,14 +449,14 @@ def main():
     device = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
-    W = max(3, args.warmup)
+    W = max(5, args.warmup)  # >= 3 eager steps + the CUDA-graph capture + one replay happen before the timed region
     K = args.steps
     B, R = (args.batch or cfg["batch"]), cfg["res"]
 
     tr = vt.Trainer(device, vae_resolution=256, vae_ch=CFG["vae_ch"], vae_ch_mult=CFG["vae_ch_mult"],
                     vae_num_res_blocks=CFG["vae_num_res_blocks"], vae_z_channels=CFG["vae_z_channels"], do_clamp=True,
                     do_ganloss=cfg["gan"], disc_type="hinge", use_lecam=cfg["gan"], max_steps=100000, lpips_eval=True,
-                    use_vq=cfg["vq"], decoder_also_perform_hr=cfg["hr"])
+                    use_vq=cfg["vq"], decoder_also_perform_hr=cfg["hr"], cuda_graph=False if args.no_graph else None)
     loader = vt.SyntheticLoader(B, R, seed=42 + rank, n_distinct=4)
     host_batches = loader.batches
     dev_batches = [b.to(device) for b in host_batches]
@@ -484,6 +485,9 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / K
     launches = (native.launch_count() - l0)
+    graphed = tr.graph_launches_per_step is not None
+    if graphed:  # replays do not pass through the C entry points: kernels per replay (counted at capture) x replays
+        launches = tr.graph_launches_per_step * K
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- timed: end to end (pinned host batch -> H2D inside, loss read back every step)
@@ -503,7 +507,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    # every rank runs the profiled extra step (it contains the NCCL collectives of a normal step); rank 0 reports it
+    # every rank runs the profiled extra step (it contains the NCCL collectives of a normal step); rank 0 reports it.
+    # It runs eagerly (per-launch CUDA events need the python wrappers), with the same kernels the graph replays.
+    tr._graph_wanted = False
     prof = profile_conv_kernels(tr, dev_batches[0])
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
@@ -538,7 +544,7 @@ def main():
                                    f"AdamW+weight re-pack (BASELINE.json configs[{cfg['idx']}]); LPIPS in eval mode "
                                    "(the reference trains with its Dropout(0.5) live; `Trainer(lpips_eval=False)` "
                                    "reproduces that)",
-                       "name": args.config, "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "name": args.config, "cuda_graph": graphed, "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "no explicit flush: per-step working set (activations ~0.9 GB/image) >> 126 MB L2",
                        "tflop_per_image": tflop},
             "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 3 * R * R * 4,

@@ -276,7 +276,8 @@ int vqb_adamw_flat_dev(float* params, const float* grads, float* exp_avg, float*
 
 /*
  * Re-pack every cached bf16 GEMM operand of the fp32 OIHW master weights in one launch (after an optimizer step).
- * jobs_dev: DEVICE array of njobs descriptors; total_blocks = sum over jobs of ceil(R*nslots*Kpad / 2048).
+ * jobs_dev: DEVICE array of njobs descriptors; total_blocks = sum over jobs of ceil(R/8)*ceil(Kpad/64)
+ * (R = Cin if transpose else Cout; one block packs an 8-row x 64-k tile for every slot; T <= 16).
  *   out[r*ld_r + (slot/sg)*ld_g + (slot%sg)*Kpad + k] = bf16(transpose ? w[k][r][.] : w[r][k][.]); fold: tapmap entries are
  *   bit masks of taps summed in fp32 (vqb_pack_weights_fold), else tap indices (vqb_pack_weights).
  * Replaces: the per-step fp32->bf16 weight casts of torch.autocast (vae_trainer.py:453,623).
@@ -286,7 +287,7 @@ typedef struct VqbPackJob {
     void* out;
     const int* tapmap;
     int32_t Cout, Cin, T, nslots, transpose, Kpad, fold, sg, ld_g, ld_r;
-    int32_t first_block; /* prefix sum of ceil(total/2048) over the preceding jobs */
+    int32_t first_block; /* prefix sum of the tile-block counts of the preceding jobs */
     int32_t _pad;
 } VqbPackJob;
 int vqb_pack_weights_multi(const VqbPackJob* jobs_dev, int njobs, int total_blocks, void* stream);

@@ -210,7 +210,10 @@ def test_flux_generator_step_vs_reference_golden(flux_models, gan, batch):
     # positive post-ReLU features): the mean inherits the per-logit error level, 1.5e-2 for this implementation AND for
     # eager bf16 D (test_flux_discriminator_step...), hence the 2e-2 floor with the GAN term, 5e-3 without
     assert _bound(ep, M["ep"], 5e-3) and _bound(el, max(M["el"], Bf["el"]), 2e-2 if gan else 5e-3), "losses"
-    assert _bound(nr_dec.max(), M["nr_dec"].max(), 0.02) and _bound(nr_dec.mean(), M["nr_dec"].mean(), 0.01), "dec norms"
+    # with the GAN term every gradient first crosses the 13 bf16 layers of the discriminator, which the "mix" peer runs
+    # in TF32: the decoder quantities are then bounded by the all-bf16 peer as well
+    D = Bf if gan else M
+    assert _bound(nr_dec.max(), D["nr_dec"].max(), 0.02) and _bound(nr_dec.mean(), D["nr_dec"].mean(), 0.01), "dec norms"
     if batch == 1:
         # run-to-run spread of this implementation (fp32 atomics in the fused GroupNorm statistics reorder sums, and bf16
         # rounding amplifies that through ~60 layers): measured mean |ratio-1| 0.002-0.011 (gan) over repeated runs, so
@@ -218,7 +221,7 @@ def test_flux_generator_step_vs_reference_golden(flux_models, gan, batch):
         assert _bound(nr_enc.max(), Bf["nr_enc"].max(), 0.03 if gan else 0.02) and \
             _bound(nr_enc.mean(), Bf["nr_enc"].mean(), 0.015 if gan else 0.01), "enc norms"
     bad = [k for k in picks
-           if not _cos_bound(cos[k], (Bf if k.startswith("encoder.") else M)["cos"][k], 2e-3)]
+           if not _cos_bound(cos[k], (Bf if (gan or k.startswith("encoder.")) else M)["cos"][k], 2e-3)]
     assert not bad, [(k, cos[k], M["cos"][k], Bf["cos"][k]) for k in bad]
 
 

@@ -47,6 +47,17 @@ __device__ __forceinline__ float sigmoidf_(float x) {
 #endif
 }
 
+// tanh for the swish derivative: MUFU.TANH by default; with -DVQB_EXACT_SIGMOID the exact form through exp
+__device__ __forceinline__ float tanh_fast(float x) {
+#if VQB_EXACT_SIGMOID
+    return 2.f / (1.f + __expf(-2.f * x)) - 1.f;
+#else
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+#endif
+}
+
 // ------------------------------------------------------------------ weight packing
 // out[r][slot][k] (bf16), r < R, k < Kpad:  transpose ? w[k][r][tap] : w[r][k][tap]   (w is OIHW fp32,
 // tap = tapmap[slot] indexes KH*KW), zero for k >= K.
@@ -305,14 +316,17 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const 
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
     if (pr < R) {
-        float mean[8], rstd[8], ga[8], be[8], s1[8], s2[8];
+        // trimmed form (this kernel sat on the FP32-issue / SFU limit): h = x*a2 + b2 (= u/2), t = tanh(h),
+        // 2*silu'(u) = (1 + t)(1 + h - h t); s1 = sum 2du, s2 = sum 2du (x - mean); scaled by 1/2 and rstd/2 at the end
+        float mean[8], rstd[8], a2[8], b2[8], s1[8], s2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = cv * 8 + j, g = c / cpg;
             mean[j] = mr[(n * G + g) * 2];
             rstd[j] = mr[(n * G + g) * 2 + 1];
-            ga[j] = gamma[c];
-            be[j] = beta[c];
+            const float a = gamma[c] * rstd[j];
+            a2[j] = 0.5f * a;
+            b2[j] = 0.5f * (beta[c] - mean[j] * a);
             s1[j] = s2[j] = 0.f;
         }
         const int p0 = blockIdx.x * pix_per_chunk;
@@ -336,22 +350,22 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const 
                 cvt8(ud[k], d);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = (f[j] - mean[j]) * rstd[j];
-                    float du = d[j];
+                    float du2 = 2.f * d[j];
                     if (silu) {
-                        const float u = fmaf(xh, ga[j], be[j]);
-                        const float sg = sigmoidf_(u);
-                        du *= sg * (1.f + u * (1.f - sg));
+                        const float h = fmaf(f[j], a2[j], b2[j]);
+                        const float t = tanh_fast(h);
+                        const float r = fmaf(-h, t, h + 1.f);
+                        du2 = d[j] * fmaf(t, r, r);
                     }
-                    s1[j] += du;
-                    s2[j] += du * xh;
+                    s1[j] += du2;
+                    s2[j] = fmaf(du2, f[j] - mean[j], s2[j]);
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sm[(cv * 8 + j) * 2], s1[j]);
-            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], s2[j]);
+            atomicAdd(&sm[(cv * 8 + j) * 2], 0.5f * s1[j]);
+            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], 0.5f * rstd[j] * s2[j]);
         }
     }
     __syncthreads();
@@ -403,16 +417,18 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     }
     if (pr < R) {
         const int n = blockIdx.y, cpg = C / G;
-        float mean[8], rstd[8], ga[8], be[8], S1[8], S2[8], cs8[8];
+        // trimmed form: dx = 2du * (gamma rstd / 2) - rstd S1 - (x - mean) rstd^2 S2, 2du as in the reduce kernel
+        float mean[8], a2[8], b2[8], k0[8], k2[8], cs8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = cv * 8 + j, g = c / cpg;
             mean[j] = mr[(n * G + g) * 2];
-            rstd[j] = mr[(n * G + g) * 2 + 1];
-            S1[j] = gs[(n * G + g) * 2];
-            S2[j] = gs[(n * G + g) * 2 + 1];
-            ga[j] = gamma[c];
-            be[j] = beta[c];
+            const float rstd = mr[(n * G + g) * 2 + 1];
+            const float a = gamma[c] * rstd;
+            a2[j] = 0.5f * a;
+            b2[j] = 0.5f * (beta[c] - mean[j] * a);
+            k0[j] = -rstd * gs[(n * G + g) * 2];
+            k2[j] = -rstd * rstd * gs[(n * G + g) * 2 + 1];
             cs8[j] = 0.f;
         }
         const int p0 = blockIdx.x * pix_per_chunk;
@@ -438,14 +454,14 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
                 if (ADD) cvt8(ua[k], r);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = (f[j] - mean[j]) * rstd[j];
-                    float du = d[j];
+                    float du2 = 2.f * d[j];
                     if (silu) {
-                        const float u = fmaf(xh, ga[j], be[j]);
-                        const float sg = sigmoidf_(u);
-                        du *= sg * (1.f + u * (1.f - sg));
+                        const float h = fmaf(f[j], a2[j], b2[j]);
+                        const float t = tanh_fast(h);
+                        const float rr = fmaf(-h, t, h + 1.f);
+                        du2 = d[j] * fmaf(t, rr, rr);
                     }
-                    float v = rstd[j] * (du * ga[j] - S1[j] - xh * S2[j]);
+                    float v = fmaf(du2, a2[j], fmaf(f[j] - mean[j], k2[j], k0[j]));
                     if (ADD) v += r[j];
                     f[j] = v;
                     // column sums of the bf16 values actually written (= bias gradient of the conv that produced x)
@@ -512,82 +528,76 @@ __global__ void __launch_bounds__(256, 2)
 gn_bwd_persistent_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                          const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
                          const float* __restrict__ mr, const float* __restrict__ gamma, const float* __restrict__ beta,
-                         float* cs /* [N][C][2], zeroed */, int* done /* [N], zeroed */, float* __restrict__ colsum,
-                         int N, int HW, int C, int G, int units, int pix_per_unit) {
-    extern __shared__ float sm[];  // [2C] partial sums | [C] dx column sums (A phase) ; then [2G] group sums
+                         float* cs /* [N][C][2], zeroed */, int* done /* [groups], zeroed */,
+                         float* __restrict__ colsum, int N, int HW, int C, int G, int S /* samples per group */,
+                         int ups /* units per sample */, int pix_per_unit, int depth, int hints) {
+    extern __shared__ float sm[];  // [2C] partial sums | [C] dx column sums ; then [2G] group sums
     float* sm_gs = sm + 2 * C;
     const int V = C >> 3, R = blockDim.x / V;
     const int cv = threadIdx.x % V, pr = threadIdx.x / V;
     const int cpg = C / G;
-    const bool worker = pr < R;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
-    float ga[8], be[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        ga[j] = gamma[cv * 8 + j];
-        be[j] = beta[cv * 8 + j];
-    }
+    const int ngroups = (N + S - 1) / S;
     float csum[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) csum[j] = 0.f;
 
-    for (int step = 0; step <= N; ++step) {
-        // ---------------------------------------------------------------- R(step)
-        if (step < N) {
-            const int n = step;
-            float mean[8], a2[8], b2[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int g = (cv * 8 + j) / cpg;
-                mean[j] = mr[(n * G + g) * 2];
-                const float a = ga[j] * mr[(n * G + g) * 2 + 1];
-                a2[j] = 0.5f * a;
-                b2[j] = 0.5f * (be[j] - mean[j] * a);
-            }
-            const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+    for (int step = 0; step < ngroups + depth; ++step) {
+        // ---------------------------------------------------------------- R(step): statistics of sample group `step`
+        if (step < ngroups) {
+            const int n0 = step * S, ns = min(S, N - n0), units = ns * ups;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int n = n0 + u / ups, ch = u % ups;
+                float mean[8], a2[8], b2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = (cv * 8 + j) / cpg;
+                    mean[j] = mr[(n * G + g) * 2];
+                    const float a = __ldg(gamma + cv * 8 + j) * mr[(n * G + g) * 2 + 1];
+                    a2[j] = 0.5f * a;
+                    b2[j] = 0.5f * (__ldg(beta + cv * 8 + j) - mean[j] * a);
+                }
+                const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
                 for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
                 __syncthreads();
-                if (worker) {
-                    float s1[8], s2[8];
+                float s1[8], s2[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-                    const int p0 = u * pix_per_unit, p1 = min(HW, p0 + pix_per_unit);
-                    for (int p = p0 + pr; p < p1; p += 4 * R) {
-                        uint4 ux[4], ud[4];
+                for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+                const int p0 = ch * pix_per_unit, p1 = min(HW, p0 + pix_per_unit);
+                for (int p = p0 + pr; p < p1; p += 3 * R) {
+                    uint4 ux[3], ud[3];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const bool in = (p + k * R) < p1;
-                            ux[k] = in ? ldg16_hint(x + base + static_cast<int64_t>(p + k * R) * C, pol_keep)
-                                       : make_uint4(0, 0, 0, 0);
-                            ud[k] = in ? ldg16_hint(dy + base + static_cast<int64_t>(p + k * R) * C, pol_keep)
-                                       : make_uint4(0, 0, 0, 0);
-                        }
+                    for (int k = 0; k < 3; ++k) {
+                        const bool in = (p + k * R) < p1;
+                        const __nv_bfloat16* xp = x + base + static_cast<int64_t>(p + k * R) * C;
+                        const __nv_bfloat16* dp = dy + base + static_cast<int64_t>(p + k * R) * C;
+                        ux[k] = in ? (hints ? ldg16_hint(xp, pol_keep) : ldg16(xp)) : make_uint4(0, 0, 0, 0);
+                        ud[k] = in ? (hints ? ldg16_hint(dp, pol_keep) : ldg16(dp)) : make_uint4(0, 0, 0, 0);
+                    }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if ((p + k * R) >= p1) break;
-                            float f[8], d[8];
-                            cvt8(ux[k], f);
-                            cvt8(ud[k], d);
+                    for (int k = 0; k < 3; ++k) {
+                        if ((p + k * R) >= p1) break;
+                        float f[8], d[8];
+                        cvt8(ux[k], f);
+                        cvt8(ud[k], d);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float du2 = 2.f * d[j];
-                                if (SILU) {
-                                    const float h = fmaf(f[j], a2[j], b2[j]);
-                                    const float t = tanh_approx(h);
-                                    const float r = fmaf(-h, t, h + 1.f);
-                                    du2 = d[j] * fmaf(t, r, r);
-                                }
-                                s1[j] += du2;
-                                s2[j] = fmaf(du2, f[j] - mean[j], s2[j]);
+                        for (int j = 0; j < 8; ++j) {
+                            float du2 = 2.f * d[j];
+                            if (SILU) {
+                                const float h = fmaf(f[j], a2[j], b2[j]);
+                                const float t = tanh_approx(h);
+                                const float r = fmaf(-h, t, h + 1.f);
+                                du2 = d[j] * fmaf(t, r, r);
                             }
+                            s1[j] += du2;
+                            s2[j] = fmaf(du2, f[j] - mean[j], s2[j]);
                         }
                     }
+                }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        atomicAdd(&sm[(cv * 8 + j) * 2], s1[j]);
-                        atomicAdd(&sm[(cv * 8 + j) * 2 + 1], s2[j]);
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    atomicAdd(&sm[(cv * 8 + j) * 2], s1[j]);
+                    atomicAdd(&sm[(cv * 8 + j) * 2 + 1], s2[j]);
                 }
                 __syncthreads();
                 for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
@@ -598,94 +608,97 @@ gn_bwd_persistent_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
                 }
                 __threadfence();
                 __syncthreads();
-                if (threadIdx.x == 0) atomicAdd(&done[n], 1);
+                if (threadIdx.x == 0) atomicAdd(&done[step], 1);
             }
         }
-        // ---------------------------------------------------------------- A(step - 1)
-        if (step >= 1) {
-            const int n = step - 1;
-            bool mine = false;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) mine = true;
-            if (mine) {
+        // ---------------------------------------------------------------- A(step - depth): dx of that sample group
+        if (step >= depth) {
+            const int gi = step - depth;
+            const int n0 = gi * S, ns = min(S, N - n0), units = ns * ups;
+            if (static_cast<int>(blockIdx.x) < units) {
                 if (threadIdx.x == 0) {
                     int v;
                     do {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + n) : "memory");
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + gi) : "memory");
                     } while (v < units);
                 }
                 __syncthreads();
-                // group sums gs[g] = (sum_c gamma_c cs0, sum_c gamma_c cs1) / m from the now complete cs[n]
-                for (int g = threadIdx.x; g < G; g += blockDim.x) {
-                    float a = 0.f, b = 0.f;
-                    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-                        a = fmaf(gamma[c], __ldcg(&cs[(static_cast<int64_t>(n) * C + c) * 2]), a);
-                        b = fmaf(gamma[c], __ldcg(&cs[(static_cast<int64_t>(n) * C + c) * 2 + 1]), b);
+                int cur_n = -1;
+                float mean[8], a2[8], b2[8], k0[8], k2[8];  // (du2 * a2 = du * gamma * rstd)
+                for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                    const int n = n0 + u / ups, ch = u % ups;
+                    if (n != cur_n) {
+                        cur_n = n;
+                        __syncthreads();
+                        // group sums gs[g] = (sum_c gamma_c cs0, sum_c gamma_c cs1) / m from the complete cs[n]
+                        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+                            float a = 0.f, b = 0.f;
+                            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                                a = fmaf(gamma[c], __ldcg(&cs[(static_cast<int64_t>(n) * C + c) * 2]), a);
+                                b = fmaf(gamma[c], __ldcg(&cs[(static_cast<int64_t>(n) * C + c) * 2 + 1]), b);
+                            }
+                            const float m = static_cast<float>(cpg) * HW;
+                            sm_gs[g * 2] = a / m;
+                            sm_gs[g * 2 + 1] = b / m;
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int g = (cv * 8 + j) / cpg;
+                            mean[j] = mr[(n * G + g) * 2];
+                            const float rstd = mr[(n * G + g) * 2 + 1];
+                            const float a = __ldg(gamma + cv * 8 + j) * rstd;
+                            a2[j] = 0.5f * a;
+                            b2[j] = 0.5f * (__ldg(beta + cv * 8 + j) - mean[j] * a);
+                            k0[j] = -rstd * sm_gs[g * 2];
+                            k2[j] = -rstd * rstd * sm_gs[g * 2 + 1];
+                        }
                     }
-                    const float m = static_cast<float>(cpg) * HW;
-                    sm_gs[g * 2] = a / m;
-                    sm_gs[g * 2 + 1] = b / m;
-                }
-                __syncthreads();
-                float mean[8], a2[8], b2[8], k0[8], k1[8], k2[8];
+                    const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
+                    const int p0 = ch * pix_per_unit, p1 = min(HW, p0 + pix_per_unit);
+                    constexpr int U = 2;
+                    for (int pp = p0 + pr; pp < p1; pp += U * R) {
+                        uint4 ux[U], ud[U], ua[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int g = (cv * 8 + j) / cpg;
-                    mean[j] = mr[(n * G + g) * 2];
-                    const float rstd = mr[(n * G + g) * 2 + 1];
-                    const float a = ga[j] * rstd;
-                    a2[j] = 0.5f * a;
-                    b2[j] = 0.5f * (be[j] - mean[j] * a);
-                    k1[j] = 0.5f * a;                        // du2 * k1 = du * gamma * rstd
-                    k0[j] = -rstd * sm_gs[g * 2];
-                    k2[j] = -rstd * rstd * sm_gs[g * 2 + 1];
-                }
-                const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
-                if (worker) {
-                    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                        const int p0 = u * pix_per_unit, p1 = min(HW, p0 + pix_per_unit);
-                        constexpr int U = ADD ? 2 : 3;
-                        for (int pp = p0 + pr; pp < p1; pp += U * R) {
-                            uint4 ux[U], ud[U], ua[U];
+                        for (int k = 0; k < U; ++k) {
+                            const bool in = (pp + k * R) < p1;
+                            const int64_t off = base + static_cast<int64_t>(pp + k * R) * C;
+                            ux[k] = in ? (hints ? ldg16_hint(x + off, pol_drop) : ldg16(x + off)) : make_uint4(0, 0, 0, 0);
+                            ud[k] = in ? (hints ? ldg16_hint(dy + off, pol_drop) : ldg16(dy + off)) : make_uint4(0, 0, 0, 0);
+                            if (ADD) ua[k] = in ? ldg16(add + off) : make_uint4(0, 0, 0, 0);
+                        }
 #pragma unroll
-                            for (int k = 0; k < U; ++k) {
-                                const bool in = (pp + k * R) < p1;
-                                const int64_t off = base + static_cast<int64_t>(pp + k * R) * C;
-                                ux[k] = in ? ldg16_hint(x + off, pol_drop) : make_uint4(0, 0, 0, 0);
-                                ud[k] = in ? ldg16_hint(dy + off, pol_drop) : make_uint4(0, 0, 0, 0);
-                                if (ADD) ua[k] = in ? ldg16_hint(add + off, pol_drop) : make_uint4(0, 0, 0, 0);
-                            }
+                        for (int k = 0; k < U; ++k) {
+                            if ((pp + k * R) >= p1) break;
+                            float f[8], d[8], r8[8];
+                            cvt8(ux[k], f);
+                            cvt8(ud[k], d);
+                            if (ADD) cvt8(ua[k], r8);
 #pragma unroll
-                            for (int k = 0; k < U; ++k) {
-                                if ((pp + k * R) >= p1) break;
-                                float f[8], d[8], r8[8];
-                                cvt8(ux[k], f);
-                                cvt8(ud[k], d);
-                                if (ADD) cvt8(ua[k], r8);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float du2 = 2.f * d[j];
-                                    if (SILU) {
-                                        const float h = fmaf(f[j], a2[j], b2[j]);
-                                        const float t = tanh_approx(h);
-                                        const float r = fmaf(-h, t, h + 1.f);
-                                        du2 = d[j] * fmaf(t, r, r);
-                                    }
-                                    float v = fmaf(du2, k1[j], fmaf(f[j] - mean[j], k2[j], k0[j]));
-                                    if (ADD) v += r8[j];
-                                    f[j] = v;
-                                    csum[j] += __bfloat162float(__float2bfloat16(v));
+                            for (int j = 0; j < 8; ++j) {
+                                float du2 = 2.f * d[j];
+                                if (SILU) {
+                                    const float h = fmaf(f[j], a2[j], b2[j]);
+                                    const float t = tanh_approx(h);
+                                    const float r = fmaf(-h, t, h + 1.f);
+                                    du2 = d[j] * fmaf(t, r, r);
                                 }
-                                uint4 o;
-                                o.x = pack_bf16x2(f[0], f[1]);
-                                o.y = pack_bf16x2(f[2], f[3]);
-                                o.z = pack_bf16x2(f[4], f[5]);
-                                o.w = pack_bf16x2(f[6], f[7]);
-                                stg16_hint(dx + base + static_cast<int64_t>(pp + k * R) * C, o, pol_drop);
+                                float v = fmaf(du2, a2[j], fmaf(f[j] - mean[j], k2[j], k0[j]));
+                                if (ADD) v += r8[j];
+                                f[j] = v;
+                                csum[j] += __bfloat162float(__float2bfloat16(v));
                             }
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]);
+                            o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]);
+                            o.w = pack_bf16x2(f[6], f[7]);
+                            __nv_bfloat16* op = dx + base + static_cast<int64_t>(pp + k * R) * C;
+                            if (hints) stg16_hint(op, o, pol_drop); else *reinterpret_cast<uint4*>(op) = o;
                         }
                     }
                 }
-                __syncthreads();  // sm_gs is rewritten by the next sample
+                __syncthreads();
             }
         }
     }
@@ -693,10 +706,8 @@ gn_bwd_persistent_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
     if (colsum) {
         for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
         __syncthreads();
-        if (worker) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], csum[j]);
-        }
+        for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], csum[j]);
         __syncthreads();
         for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], sm[i]);
     }
@@ -1077,16 +1088,23 @@ static int gn_silu_bwd_impl(const void* x, const void* dy, const void* add, void
     float* gsum = ws;
     // Persistent L2-pipelined form (reduce + apply in one launch, x / dy read from HBM once): used when one sample's
     // x + dy (+ add) comfortably fits the L2 next to the following sample's, and there is enough work to pipeline.
-    static const bool persistent_on = [] {
+    // VQB_GN_BWD_PERSISTENT=1 opts into the persistent form. Measured (tools/gn_bwd_bench.py, N=32, profiles/
+    // r02_gn_bwd_variants.txt): 1.5-2x SLOWER than the two-kernel form on every shape (e.g. 128 ch @ 256^2: 1010 us vs
+    // 682 us) — two 128-register CTAs per SM keep too few loads in flight and every unit pays barrier + fence + atomics —
+    // so the default stays the two-kernel form.
+    static const int gnp_mode = [] {
         const char* e = getenv("VQB_GN_BWD_PERSISTENT");
-        return !(e && e[0] == '0');
+        return e ? atoi(e) : 0;
     }();
+    static const int gnp_depth = [] { const char* e = getenv("VQB_GNP_DEPTH"); return e ? atoi(e) : 1; }();
+    static const int gnp_hints = [] { const char* e = getenv("VQB_GNP_HINTS"); return e ? atoi(e) : 1; }();
+    static const int gnp_mb = [] { const char* e = getenv("VQB_GNP_MB"); return e ? atoi(e) : 36; }();
     const int64_t sample_bytes = static_cast<int64_t>(HW) * C * 2 * (add ? 3 : 2);
-    if (!cs_pre && persistent_on && T <= 256 && sample_bytes <= (40ll << 20) && N >= 2 &&
-        static_cast<int64_t>(HW) * C >= (1 << 16)) {
+    if (!cs_pre && gnp_mode && T <= 256 && T % (C / 8) == 0 && sample_bytes <= (static_cast<int64_t>(gnp_mb) << 20) &&
+        static_cast<int64_t>(N) * HW * C >= (1 << 18)) {
         const int V = C / 8, R = T / V;
         float* csw = ws;                                                   // [N][C][2]
-        int* done = reinterpret_cast<int*>(ws + static_cast<int64_t>(N) * C * 2);  // [N] (<= N*G*2 floats of ws)
+        int* done = reinterpret_cast<int*>(ws + static_cast<int64_t>(N) * C * 2);  // [<= N] (ws has N*G*2 floats there)
         VQB_CUDA(cudaMemsetAsync(csw, 0, sizeof(float) * (2 * N * C + N), st));
         if (dx_colsum) VQB_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
         const size_t smem = (2 * C + 2 * G) * sizeof(float);
@@ -1096,15 +1114,21 @@ static int gn_silu_bwd_impl(const void* x, const void* dy, const void* add, void
                 return set_error(VQB_ECUDA, "vqb_gn_silu_bwd: occupancy query failed");
             if (bpsm > 2) bpsm = 2;
             const int grid = (num_sms() > 0 ? num_sms() : 148) * bpsm;
-            int units = grid;  // one R unit and one A unit per CTA and sample when the sample is large enough
+            // sample groups of S samples whose x + dy (+ add) fit the L2 budget; each group is cut into ~grid units
+            int S = static_cast<int>((static_cast<int64_t>(gnp_mb) << 20) / sample_bytes);
+            if (S < 1) S = 1;
+            if (S > N) S = N;
             const int min_ppu = R * 4;
-            if (HW / units < min_ppu) units = HW / min_ppu > 0 ? HW / min_ppu : 1;
-            int ppu = (HW + units - 1) / units;
+            int ups = (grid + S - 1) / S;  // units per sample
+            if (ups < 1) ups = 1;
+            if (HW / ups < min_ppu) ups = HW / min_ppu > 0 ? HW / min_ppu : 1;
+            int ppu = (HW + ups - 1) / ups;
             ppu = ((ppu + R - 1) / R) * R;
-            units = (HW + ppu - 1) / ppu;
+            ups = (HW + ppu - 1) / ppu;
             kern<<<grid, T, smem, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
                                         static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), mr,
-                                        gamma, beta, csw, done, dx_colsum, N, HW, C, G, units, ppu);
+                                        gamma, beta, csw, done, dx_colsum, N, HW, C, G, S, ups, ppu, gnp_depth,
+                                        gnp_hints);
             return VQB_OK;
         };
         int rc;

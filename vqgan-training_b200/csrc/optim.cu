@@ -72,12 +72,19 @@ struct PackJob {
     __nv_bfloat16* out;
     const int* tapmap;
     int Cout, Cin, T, nslots, transpose, Kpad, fold, sg, ld_g, ld_r;
-    int first_block;  // prefix sum of 2048-element blocks over the jobs before this one
+    int first_block;  // prefix sum of ceil(R/8)*ceil(Kpad/64) tile blocks over the jobs before this one
     int _pad;
 };
 static_assert(sizeof(PackJob) == sizeof(VqbPackJob), "PackJob must mirror VqbPackJob");
 
+// One block = an (8 rows) x (64 k) tile of one job, all slots: the OIHW source is read in contiguous runs (64*T floats per
+// row for the forward layout, 8*T floats per k for the transposed one) into shared memory, then every slot's 64
+// consecutive bf16 (128 B) are written coalesced. (The first version read with a stride of T floats: 1.14 ms per step
+// for 0.65 GB of weights; this form is HBM/L2 streaming.)
+constexpr int kPackRows = 8, kPackK = 64, kPackMaxT = 16;
+
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    __shared__ float tile[kPackRows * kPackK * kPackMaxT];
     // binary search: last job with first_block <= blockIdx.x
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
@@ -87,28 +94,46 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJob* 
     const PackJob jb = jobs[lo];
     const int R = jb.transpose ? jb.Cin : jb.Cout;
     const int K = jb.transpose ? jb.Cout : jb.Cin;
-    const int64_t total = static_cast<int64_t>(R) * jb.nslots * jb.Kpad;
-    const int64_t base = static_cast<int64_t>(blockIdx.x - jb.first_block) * 2048;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int64_t i = base + u * 256 + threadIdx.x;
-        if (i >= total) break;
-        const int k = static_cast<int>(i % jb.Kpad);
-        const int slot = static_cast<int>((i / jb.Kpad) % jb.nslots);
-        const int r = static_cast<int>(i / (static_cast<int64_t>(jb.Kpad) * jb.nslots));
-        float val = 0.f;
-        if (k < K) {
-            const int co = jb.transpose ? k : r, ci = jb.transpose ? r : k;
-            const float* wp = jb.w + (static_cast<int64_t>(co) * jb.Cin + ci) * jb.T;
-            const int tm = jb.tapmap[slot];
-            if (jb.fold) {
-                for (int t = 0; t < jb.T; ++t)
-                    if ((tm >> t) & 1) val += wp[t];
-            } else {
-                val = wp[tm];
-            }
+    const int T = jb.T;
+    const int kblocks = (jb.Kpad + kPackK - 1) / kPackK;
+    const int bid = static_cast<int>(blockIdx.x) - jb.first_block;
+    const int r0 = (bid / kblocks) * kPackRows, k0 = (bid % kblocks) * kPackK;
+    // ---- load: tile[(r*64 + k)*T + t]
+    const int total = kPackRows * kPackK * T;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        int r, k, t;
+        if (!jb.transpose) {  // contiguous in (k, t) for a fixed row
+            t = e % T;
+            k = (e / T) % kPackK;
+            r = e / (T * kPackK);
+        } else {  // contiguous in (r, t) for a fixed k
+            t = e % T;
+            r = (e / T) % kPackRows;
+            k = e / (T * kPackRows);
         }
-        jb.out[static_cast<int64_t>(r) * jb.ld_r + (slot / jb.sg) * jb.ld_g + (slot % jb.sg) * jb.Kpad + k] =
+        float v = 0.f;
+        if (r0 + r < R && k0 + k < K) {
+            const int co = jb.transpose ? k0 + k : r0 + r, ci = jb.transpose ? r0 + r : k0 + k;
+            v = jb.w[(static_cast<int64_t>(co) * jb.Cin + ci) * T + t];
+        }
+        tile[(r * kPackK + k) * T + t] = v;
+    }
+    __syncthreads();
+    // ---- store: 64 consecutive k per (row, slot)
+    const int nout = kPackRows * jb.nslots * kPackK;
+    for (int e = threadIdx.x; e < nout; e += blockDim.x) {
+        const int k = e % kPackK, slot = (e / kPackK) % jb.nslots, r = e / (kPackK * jb.nslots);
+        if (r0 + r >= R || k0 + k >= jb.Kpad) continue;
+        const float* tp = tile + (r * kPackK + k) * T;
+        const int tm = jb.tapmap[slot];
+        float val = 0.f;
+        if (jb.fold) {
+            for (int t = 0; t < T; ++t)
+                if ((tm >> t) & 1) val += tp[t];
+        } else {
+            val = tp[tm];
+        }
+        jb.out[static_cast<int64_t>(r0 + r) * jb.ld_r + (slot / jb.sg) * jb.ld_g + (slot % jb.sg) * jb.Kpad + k0 + k] =
             __float2bfloat16(val);
     }
 }
@@ -184,7 +209,7 @@ int vqb_adamw_flat_dev(float* params, const float* grads, float* exp_avg, float*
 }
 
 int vqb_pack_weights_multi(const VqbPackJob* jobs_dev, int njobs, int total_blocks, void* stream) {
-    VQB_CHECK(jobs_dev && njobs >= 1 && total_blocks >= 1, "vqb_pack_weights_multi: bad arguments");
+    VQB_CHECK(jobs_dev && njobs >= 1 && total_blocks >= 1, "vqb_pack_weights_multi: bad arguments");  // (T <= 16 per job)
     pack_weights_multi_kernel<<<total_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const PackJob*>(jobs_dev), njobs);
     VQB_CUDA(cudaGetLastError());

@@ -73,9 +73,10 @@ class _PackEntry:
                                  T=T, nslots=nslots, transpose=transpose, Kpad=Kpad, fold=fold, sg=sg, ld_g=ld_g,
                                  ld_r=ld_r, first_block=first_block, _pad=0)
 
-    def blocks(self):
+    def blocks(self):  # one block = an 8-row x 64-k tile, all slots (csrc/optim.cu)
         Cout, Cin, T, nslots, transpose, Kpad = self.spec[:6]
-        return -(-((Cin if transpose else Cout) * nslots * Kpad) // 2048)
+        assert T <= 16
+        return -(-(Cin if transpose else Cout) // 8) * -(-Kpad // 64)
 
 
 # every live pack entry, by the data_ptr of the fp32 master weight it was packed from (weak: caches own the entries)
@@ -299,7 +300,12 @@ def conv_gnbwd_supported(g: plans.ConvGeom, Cout: int, out_strides, groups: int)
     return ok
 
 
+gnbwd_fused_launches = 0  # how many data-gradient launches carried fused GroupNorm-backward statistics (tests)
+
+
 def run_conv_gemm_gnbwd(g: plans.ConvGeom, a, wp, Cout, out, out_strides, link: "GnLink", cs):
+    global gnbwd_fused_launches
+    gnbwd_fused_launches += 1
     dk = (Cout, tuple(out_strides), 0, False)
     descs = g.__dict__.setdefault("_descs", {})
     d = descs.get(dk)
