@@ -434,12 +434,12 @@ def test_multi_pack_kernel_matches_single_tensor_pack_kernels():
              (64, 32, 4, list(range(16)), False, 32, False), (512, 512, 1, [0], True, 512, False),
              (256, 256, 3, [0b000011011, 0b000110110, 0b011011000, 0b110110000], False, 256, True),
              (130, 70, 3, list(range(9)), False, 72, False)]
-    ents, refs = [], []
+    ents, refs, keep = [], [], []
     for (Cout, Cin, k, tapmap, transpose, Kpad, fold) in cases:
         w = torch.randn(Cout, Cin, k, k, device="cuda")
+        keep.append(w)  # entries hold weak references to their weights
         ents.append(ops._new_pack_entry(w, tapmap, transpose, Kpad, fold))
         refs.append(ops.pack_weights(w, tapmap, transpose, Kpad, fold))
-        ents[-1]._keep = w
     wf = torch.randn(64, 3, 3, 3, device="cuda")
     fat = ops._new_pack_entry(wf, list(range(9)), False, 8, False, fat=True)
     ops._run_pack(ents + [fat])  # ONE launch for all jobs

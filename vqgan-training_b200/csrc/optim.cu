@@ -84,7 +84,7 @@ static_assert(sizeof(PackJob) == sizeof(VqbPackJob), "PackJob must mirror VqbPac
 constexpr int kPackRows = 8, kPackK = 64, kPackMaxT = 16;
 
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
-    __shared__ float tile[kPackRows * kPackK * kPackMaxT];
+    __shared__ float tile[kPackK * (kPackRows * kPackMaxT + 1)];
     // binary search: last job with first_block <= blockIdx.x
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
@@ -98,43 +98,50 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackJob* 
     const int kblocks = (jb.Kpad + kPackK - 1) / kPackK;
     const int bid = static_cast<int>(blockIdx.x) - jb.first_block;
     const int r0 = (bid / kblocks) * kPackRows, k0 = (bid % kblocks) * kPackK;
-    // ---- load: tile[(r*64 + k)*T + t]
-    const int total = kPackRows * kPackK * T;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        int r, k, t;
-        if (!jb.transpose) {  // contiguous in (k, t) for a fixed row
-            t = e % T;
-            k = (e / T) % kPackK;
-            r = e / (T * kPackK);
-        } else {  // contiguous in (r, t) for a fixed k
-            t = e % T;
-            r = (e / T) % kPackRows;
-            k = e / (T * kPackRows);
+    const int nr = min(kPackRows, R - r0), nk = max(0, min(kPackK, K - k0));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- load (no runtime divisions): forward layout tile[r*64T + (k*T + t)], transposed tile[k*(8T+1) + (r*T + t)]
+    if (!jb.transpose) {
+        const int run = nk * T;  // contiguous floats of one row
+        for (int r = warp; r < kPackRows; r += 8) {
+            const float* src = jb.w + (static_cast<int64_t>(r0 + r) * jb.Cin + k0) * T;
+            for (int e = lane; e < kPackK * T; e += 32) tile[r * kPackK * T + e] = (r < nr && e < run) ? src[e] : 0.f;
         }
-        float v = 0.f;
-        if (r0 + r < R && k0 + k < K) {
-            const int co = jb.transpose ? k0 + k : r0 + r, ci = jb.transpose ? r0 + r : k0 + k;
-            v = jb.w[(static_cast<int64_t>(co) * jb.Cin + ci) * T + t];
+    } else {
+        const int run = nr * T;  // contiguous floats of one k (= one output channel's rows r0..r0+7)
+        const int kstride = kPackRows * T + 1;
+        for (int k = warp; k < kPackK; k += 8) {
+            const float* src = jb.w + (static_cast<int64_t>(k0 + k) * jb.Cin + r0) * T;
+            for (int e = lane; e < kPackRows * T; e += 32) tile[k * kstride + e] = (k < nk && e < run) ? src[e] : 0.f;
         }
-        tile[(r * kPackK + k) * T + t] = v;
     }
     __syncthreads();
-    // ---- store: 64 consecutive k per (row, slot)
-    const int nout = kPackRows * jb.nslots * kPackK;
-    for (int e = threadIdx.x; e < nout; e += blockDim.x) {
-        const int k = e % kPackK, slot = (e / kPackK) % jb.nslots, r = e / (kPackK * jb.nslots);
-        if (r0 + r >= R || k0 + k >= jb.Kpad) continue;
-        const float* tp = tile + (r * kPackK + k) * T;
-        const int tm = jb.tapmap[slot];
-        float val = 0.f;
-        if (jb.fold) {
-            for (int t = 0; t < T; ++t)
-                if ((tm >> t) & 1) val += tp[t];
-        } else {
-            val = tp[tm];
+    // ---- store: thread = (row pair q, k); every (row, slot) writes 64 consecutive bf16
+    const int k = threadIdx.x & (kPackK - 1), q = threadIdx.x >> 6;
+    if (k0 + k < jb.Kpad) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = q * 2 + rr;
+            if (r >= nr) break;
+            const float* tp = jb.transpose ? tile + k * (kPackRows * T + 1) + r * T : tile + (r * kPackK + k) * T;
+            __nv_bfloat16* orow = jb.out + static_cast<int64_t>(r0 + r) * jb.ld_r + k0 + k;
+            int sl = 0, grp = 0;  // slot within its group, group index (no divisions)
+            for (int slot = 0; slot < jb.nslots; ++slot) {
+                const int tm = jb.tapmap[slot];
+                float val = 0.f;
+                if (jb.fold) {
+                    for (int t = 0; t < T; ++t)
+                        if ((tm >> t) & 1) val += tp[t];
+                } else {
+                    val = tp[tm];
+                }
+                orow[grp * jb.ld_g + sl * jb.Kpad] = __float2bfloat16(val);
+                if (++sl == jb.sg) {
+                    sl = 0;
+                    ++grp;
+                }
+            }
         }
-        jb.out[static_cast<int64_t>(r0 + r) * jb.ld_r + (slot / jb.sg) * jb.ld_g + (slot % jb.sg) * jb.Kpad + k0 + k] =
-            __float2bfloat16(val);
     }
 }
 
