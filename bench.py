@@ -305,7 +305,7 @@ def eager_b200_leg(cfg, B, world, rank, device, steps, warmup):
             gs = [p.grad for p in params if p.grad is not None]
             flat = torch.cat([x.reshape(-1) for x in gs])
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            torch._foreach_copy_(gs, list(flat.split([x.numel() for x in gs])))
+            torch._foreach_copy_(gs, [v.view_as(x) for v, x in zip(flat.split([x.numel() for x in gs]), gs)])
 
     def avg_fn(n):
         if world > 1:
@@ -516,6 +516,7 @@ def main():
     # ---------------- the PyTorch-eager-on-B200 peer (same step, same batch, same GPUs), after freeing our own state
     eager = None
     if not args.no_eager:
+        tr._graph = None
         del tr, out, o, dev_batches, loader
         import gc
 
@@ -586,6 +587,13 @@ def main():
                                               f"of the reference arithmetic, torch CPU fp32, {threads} threads); the "
                                               "reference tree is unpackaged Python and cannot be installed/travel"}
         emit_json(line)
+    # release the captured step (its graph holds NCCL work) before tearing the process group down: with a live graph
+    # destroy_process_group() hung until the launcher's timeout (N=2, round 2)
+    tr = None
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -166,7 +166,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     const int num_kb = p.ntaps * p.kchunks;
 
-    if (warp == 0 && lane == 0 && p.halo) {
+    // The single-thread roles are entered through elect.sync (not `lane == 0`): ptxas then knows the region runs in
+    // exactly one lane with warp-uniform operands and emits the TMA / tcgen05 instructions back to back from uniform
+    // registers. With `lane == 0` every UTCHMMA was wrapped in an ELECT / PLOP3 / BRA.U.ANY loop plus R2UR moves — ~190
+    // SASS instructions per tap in the issue thread, 1058 cycles per tap against the 512 the tensor core needs
+    // (ncu source-level sampling, profiles/r02_ncu_conv128_issue_bound.txt): the issue thread, not shared memory, was
+    // what held the 128-channel layers at ~50 % tensor-pipe utilisation.
+    if (warp == 0) {
+      if (elect_one()) {
+      if (p.halo) {
         // ===================== TMA producer, halo mode: per 64-channel chunk ONE activation box (tile + halo) and one
         // weight tile per tap. The activation bytes per FLOP drop by ~ntaps/1.3; the weight tiles stream through
         // their own ring.
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 0 && lane == 0) {
+      } else {
         // ===================== TMA producer (one thread; keep the per-K-block instruction count small) =========
         uint32_t stage = 0, phase = 0, tile_iter = 0;
         uint8_t* a_dst = sA;
@@ -271,7 +279,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && crank == 0) {
+      }
+      }
+    } else if (warp == 1) {
+      if (crank == 0 && elect_one()) {
         // ===================== MMA issuer (single thread; in pair mode only the leader CTA's) =====================
         // This thread must issue 4*mtiles MMAs per K-block in well under the ~512*mtiles cycles the tensor core needs
         // for them: descriptors are base + increments (no divisions, no per-K-block descriptor builds).
@@ -390,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (two) umma_commit(&tfull[b1]);
             }
         }
+      }
     } else if (warp >= 4) {
         // ===================== epilogue (4 warps = 128 accumulator rows) =====================
         const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read

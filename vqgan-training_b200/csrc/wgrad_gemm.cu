@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
         kb1 = static_cast<int>((static_cast<int64_t>(p.pixel_boxes) * (s + 1)) / p.ksplit);
     };
 
-    if (warp == 0 && lane == 0) {
+    // single-thread roles are entered through elect.sync so that ptxas emits the TMA / tcgen05 instructions from uniform
+    // registers without per-instruction ELECT loops (see conv_gemm.cu)
+    if (warp == 0) {
+      if (elect_one()) {
         // ===================== TMA producer =====================
         uint32_t stage = 0, phase = 0;
         for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
@@ -147,7 +150,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
         // ===================== MMA issuer (lean: descriptors are base + increments) =====================
         const uint32_t idesc = make_idesc_bf16(kWM, p.block_n, 1, 1);  // both operands MN-major
         // MN-major, 128B swizzle: SBO = 8 K-rows (1024 B), LBO = next 64-wide MN atom (atom_bytes)
@@ -203,6 +208,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
             if (two) umma_commit(&tfull[1]);
             umma_commit(&tfull[as]);
         }
+      }
     } else if (warp >= 4) {
         // ===================== epilogue: fp32 partial tile -> global =====================
         const uint32_t ew = warp - 4;

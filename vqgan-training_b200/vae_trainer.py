@@ -504,6 +504,13 @@ class Trainer:
         g.replay()
         return out
 
+    def release_graph(self):
+        """Drops the captured step (and the memory pool it pins). Call before destroying the process group."""
+        self._graph = None
+        self._graph_wanted = False
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     @property
     def graph_launches_per_step(self):
         """Kernels of libvqb200.so inside one replay of the captured step (None while running eagerly)."""
@@ -776,6 +783,7 @@ def train_ddp(dataset_url, test_dataset_url, num_epochs, batch_size, do_ganloss,
                 print(f"Saved checkpoint to {ck}")
         if done:
             break
+    tr.release_graph()  # a live CUDA graph holds NCCL work: release it before the process group goes away
     cleanup()
 
 
