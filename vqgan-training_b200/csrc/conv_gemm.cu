@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace vqb {
 
 constexpr int kBlockM = 128;
@@ -947,7 +949,13 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     // (Cout < 128: 64-column MMAs are issue/smem bound either way and the per-tap path measured ~10 % faster)
     //  Cout <= 32 (decoder conv_out, data gradients of 3-channel layers; any output format, direct-store epilogue): the
     //  nine-fold L2->SM re-read of the activations is all there is to save, so the halo wins there too)
-    const bool halo_big = d->oc == 1 && !d->out_f32 && d->Cout % 16 == 0 && d->Cout >= 128 && !(p_dbg & 256);
+    // (round 2: with the issue thread no longer the limiter the halo tile also wins for 64-channel outputs — VGG 64->64 @
+    //  256^2 — VQB_HALO_MIN_COUT overrides the threshold for A/B measurements)
+    static const int halo_min_cout = [] {
+        const char* e = getenv("VQB_HALO_MIN_COUT");
+        return e ? atoi(e) : 128;
+    }();
+    const bool halo_big = d->oc == 1 && !d->out_f32 && d->Cout % 16 == 0 && d->Cout >= halo_min_cout && !(p_dbg & 256);
     bool halo = !(p_dbg & 1024) && d->nviews == 1 && d->ntaps >= 2 && d->C % 64 == 0 && d->W > 8 && d->H > 8 &&
                 (halo_big || d->Cout <= 32);
     int dwmin = 0, dwmax = 0, dhmin = 0, dhmax = 0;
