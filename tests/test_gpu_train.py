@@ -215,7 +215,10 @@ def test_two_rank_nccl_gradients_equal_single_rank_full_batch():
     c_all = float(np.dot(g0, ref) / (np.linalg.norm(g0) * np.linalg.norm(ref)))
     print(f"\nN=2 vs N=1 full batch: decoder-grad rel err {e_dec:.3e} at common GradNorm scale {scale:.4f}; "
           f"cosine over all {ref.size} gradient elements {c_all:.6f}")
-    assert e_dec < 5e-3 and c_all > 0.99
+    # measured 4.5e-3: the two sides run different per-rank batch sizes (2 vs 4 samples per tile stream), so the fused
+    # GroupNorm statistics sum in a different order and bf16 rounding turns that into ~0.5 % noise; exact logic errors
+    # (a missed slot, a wrong average) show up as O(1)
+    assert e_dec < 1.5e-2 and c_all > 0.999
 
 
 def test_lpips_train_mode_dropout_matches_reference_arithmetic_with_same_mask():

@@ -597,16 +597,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         const int col = col0 + c0;
                         float f[16];
                         const bool have = (c4 < 2) ? h0 : h1;
+                        if (have) {  // uniform branch (no per-element selects: the epilogue is close to critical)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t raw = (c4 < 2) ? v0[(c4 & 1) * 16 + j] : v1[(c4 & 1) * 16 + j];
-                            f[j] = have ? __uint_as_float(raw) : 0.f;
+                            for (int j = 0; j < 16; ++j)
+                                f[j] = __uint_as_float((c4 < 2) ? v0[(c4 & 1) * 16 + j] : v1[(c4 & 1) * 16 + j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = 0.f;
                         }
                         const bool live = (col + 16 <= p.Cout);  // uniform (Cout % 16 == 0 on this path)
                         if (live) {
-                            if (has_bias) {
+                            if (has_bias) {  // 16 channels = four 16-byte loads (col % 16 == 0, bias base 16-byte aligned)
+                                const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const float4 b4 = __ldg(bp + j4);
+                                    f[4 * j4] += b4.x;
+                                    f[4 * j4 + 1] += b4.y;
+                                    f[4 * j4 + 2] += b4.z;
+                                    f[4 * j4 + 3] += b4.w;
+                                }
                             }
                             if (has_res && (valid || p.aux_tma == 1)) {
                                 uint4 r0, r1;
@@ -929,7 +939,9 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     VQB_CHECK(d->ntaps >= 1 && d->ntaps <= VQB_MAX_TAPS && d->nviews >= 1 && d->nviews <= VQB_MAX_VIEWS,
               "vqb_conv_gemm: ntaps=%d nviews=%d out of range", d->ntaps, d->nviews);
     VQB_CHECK(((int64_t)d->ntaps * d->C) % 8 == 0, "vqb_conv_gemm: weight row stride must be 16-byte aligned");
-    if ((d->flags & VQB_EPI_BIAS)) VQB_CHECK(bias != nullptr, "vqb_conv_gemm: VQB_EPI_BIAS without bias");
+    if ((d->flags & VQB_EPI_BIAS))
+        VQB_CHECK(bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0,
+                  "vqb_conv_gemm: VQB_EPI_BIAS needs a 16-byte aligned bias pointer");
     if ((d->flags & VQB_EPI_RES)) VQB_CHECK(res != nullptr, "vqb_conv_gemm: VQB_EPI_RES without res");
     if ((d->flags & VQB_EPI_MASK)) VQB_CHECK(mask != nullptr, "vqb_conv_gemm: VQB_EPI_MASK without mask");
     if ((d->flags & VQB_EPI_STATS)) VQB_CHECK(stats != nullptr, "vqb_conv_gemm: VQB_EPI_STATS without stats");

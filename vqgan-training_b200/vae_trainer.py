@@ -394,10 +394,10 @@ class Trainer:
         # per step otherwise keep the host within ~10 % of being the limiter. Auto-enabled (None) when no host-side
         # random branch changes the graph from step to step; VQB_CUDA_GRAPH=0 disables.
         if cuda_graph is None:
-            # multi-rank: the captured step contains the NCCL collectives (validated at N=2: 646.9 vs 641.6 images/s), but
-            # that configuration could not be validated at N=4/8 this round, so it is opt-in there (VQB_CUDA_GRAPH=2)
+            # multi-rank: the captured step contains the NCCL collectives (N=2: 665.7 vs 659.6 images/s eager-launched;
+            # release_graph() before destroy_process_group()). VQB_CUDA_GRAPH=0 disables, =single keeps it to one rank.
             mode = os.environ.get("VQB_CUDA_GRAPH", "1")
-            cuda_graph = mode == "2" or (mode == "1" and not _dist_on())
+            cuda_graph = mode == "1" or (mode == "single" and not _dist_on())
         self._graph_wanted = bool(cuda_graph) and not (crop_invariance or flip_invariance or
                                                        augment_before_perceptual_loss)
         self._graph = None          # (key, CUDAGraph, static input, static outputs, launches per step)
