@@ -305,6 +305,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 
 // ------------------------------------------------------------------ GroupNorm backward
 // per-(n,channel) sums of du and du*xhat, du = dy * silu'(u), u = xhat*gamma + beta
+template <int U>
 __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                      const float* __restrict__ mr, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* __restrict__ cs /* [N][C][2] */, int HW,
@@ -334,16 +335,16 @@ __global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const 
         const int64_t base = (static_cast<int64_t>(n) * HW) * C + cv * 8;
         // 4 pixel rows (8 x 16-byte loads) in flight per thread: with 2 rows the kernel sat at 57 % of HBM bandwidth on
         // load latency (ncu: 16 warps/SM, long-scoreboard stalls)
-        for (int p = p0 + pr; p < p1; p += 4 * R) {
-            uint4 ux[4], ud[4];
+        for (int p = p0 + pr; p < p1; p += U * R) {
+            uint4 ux[U], ud[U];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < U; ++k) {
                 const bool in = (p + k * R) < p1;
                 ux[k] = in ? ldg16(x + base + static_cast<int64_t>(p + k * R) * C) : make_uint4(0, 0, 0, 0);
                 ud[k] = in ? ldg16(dy + base + static_cast<int64_t>(p + k * R) * C) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < U; ++k) {
                 if ((p + k * R) >= p1) break;
                 float f[8], d[8];
                 cvt8(ux[k], f);
@@ -1146,10 +1147,17 @@ static int gn_silu_bwd_impl(const void* x, const void* dy, const void* add, void
         float* csw = ws;
         gsum = ws + static_cast<int64_t>(N) * C * 2;
         VQB_CUDA(cudaMemsetAsync(csw, 0, sizeof(float) * 2 * N * C, st));
-        cv_grid(HW, C, N, gn_bwd_reduce_kernel, 2 * C * sizeof(float), chunks, ppc);
-        gn_bwd_reduce_kernel<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(
-            static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mr, gamma, beta, csw, HW, C,
-            G, ppc, silu);
+        static const int red_u = [] { const char* e = getenv("VQB_GN_RED_U"); return e ? atoi(e) : 4; }();
+        auto launch_red = [&](auto kern) {
+            cv_grid(HW, C, N, kern, 2 * C * sizeof(float), chunks, ppc);
+            kern<<<dim3(chunks, N), T, 2 * C * sizeof(float), st>>>(
+                static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), mr, gamma, beta, csw, HW,
+                C, G, ppc, silu);
+        };
+        if (red_u == 6) launch_red(gn_bwd_reduce_kernel<6>);
+        else if (red_u == 8) launch_red(gn_bwd_reduce_kernel<8>);
+        else if (red_u == 2) launch_red(gn_bwd_reduce_kernel<2>);
+        else launch_red(gn_bwd_reduce_kernel<4>);
         cs = csw;
         count_launch();
     }
