@@ -449,7 +449,8 @@ def main():
     device = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
-    W = max(5, args.warmup)  # >= 3 eager steps + the CUDA-graph capture + one replay happen before the timed region
+    W = max(3, args.warmup)
+    PREP = 0 if args.no_graph else 5  # 3 eager steps + the CUDA-graph capture + one replay, before the W warm-up steps
     K = args.steps
     B, R = (args.batch or cfg["batch"]), cfg["res"]
 
@@ -466,8 +467,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- warm-up
-    for i in range(W):
+    # ---------------- graph preparation (untimed) + warm-up
+    for i in range(PREP + W):
         tr.step(dev_batches[i % len(dev_batches)])
     barrier()
 
@@ -545,7 +546,7 @@ def main():
                                    f"AdamW+weight re-pack (BASELINE.json configs[{cfg['idx']}]); LPIPS in eval mode "
                                    "(the reference trains with its Dropout(0.5) live; `Trainer(lpips_eval=False)` "
                                    "reproduces that)",
-                       "name": args.config, "cuda_graph": graphed, "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "name": args.config, "cuda_graph": graphed, "graph_prep_steps": PREP, "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "no explicit flush: per-step working set (activations ~0.9 GB/image) >> 126 MB L2",
                        "tflop_per_image": tflop},
             "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 3 * R * R * 4,

@@ -72,6 +72,7 @@ struct alignas(64) ConvParams {
     const float* gn_beta;   // [C]
     float* gn_cs;           // [N][C][2], pre-zeroed
     int32_t gn_G, gn_lcpg;  // groups, log2(channels per group)
+    int32_t lean, _pad2;    // lean production issue loop (VQB_LEAN_ISSUE=0 selects the general one for A/B measurements)
 };
 
 // One step of the transposing butterfly used by the fused GroupNorm-backward statistics: lanes whose bit OFF is set
@@ -315,7 +316,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             tc_fence_after();
             const uint32_t d0 = tmem_base + b0 * p.block_n, d1 = tmem_base + b1 * p.block_n;
             uint32_t acc = 0;
-            if (p.halo) {
+            if (!PAIR && p.lean && p.halo && !p.swap && do_mma) {
+                // ---- production halo path, written for the shortest possible instruction stream in this one thread
+                // (ncu: the issue thread is ~78 % busy even after the elect.sync fix): loop constants in locals, 32-bit
+                // arithmetic on the descriptors' low words, next tap's descriptor offset fetched while this tap's MMAs
+                // are being issued.
+                const uint64_t dh64 = make_smem_desc(smem_u32(sA), 0, static_cast<uint32_t>(p.h_sbo), 2);
+                const uint32_t dh_lo = static_cast<uint32_t>(dh64), dh_hi = static_cast<uint32_t>(dh64 >> 32);
+                const uint32_t db_lo0 = static_cast<uint32_t>(db_base), db_hi = static_cast<uint32_t>(db_base >> 32);
+                const uint32_t h_step = static_cast<uint32_t>(p.h_bytes) >> 4;
+                const uint32_t mt_off = static_cast<uint32_t>(p.mt_dw) * 8u;
+                const int ntaps = p.ntaps, kchunks = p.kchunks;
+                const uint32_t nhst = static_cast<uint32_t>(p.h_stages);
+                uint32_t off = p.tap_off16[0];
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&hfull[hstage], hphase);
+                    const uint32_t dah_lo = dh_lo + hstage * h_step;
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_lo = dah_lo + off, b_lo = db_lo0 + b_off;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16_lohi(d0, a_lo + 2 * k, dh_hi, b_lo + 2 * k, db_hi, idesc, acc | k);
+                        if (two) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_bf16_lohi(d1, a_lo + mt_off + 2 * k, dh_hi, b_lo + 2 * k, db_hi, idesc, acc | k);
+                        }
+                        off = p.tap_off16[t + 1 < ntaps ? t + 1 : 0];  // in flight while the MMAs above are queued
+                        umma_commit(&empty[stage]);
+                        acc = 1;
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                            b_off = 0;
+                        } else {
+                            b_off += b_step;
+                        }
+                    }
+                    umma_commit(&hempty[hstage]);  // every tap of this chunk has been issued: the halo tile may be refilled
+                    if (++hstage == nhst) {
+                        hstage = 0;
+                        hphase ^= 1;
+                    }
+                }
+            } else if (p.halo) {
                 // halo mode: the A descriptor of tap t is the halo tile's descriptor plus a row offset (the 128B swizzle is
                 // a function of absolute smem address bits, so row-shifted starts and an 8-row group stride of one
                 // halo-tile line read exactly the rows the TMA unit wrote: tools/gpu_probe.py shift)
@@ -1154,6 +1200,9 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     p.bias = bias;
     p.stats = stats;
     p.dbg = debug_mode();
+    static const int lean_issue = [] { const char* e = getenv("VQB_LEAN_ISSUE"); return e ? atoi(e) : 1; }();
+    p.lean = lean_issue;
+    p._pad2 = 0;
     for (int t = 0; t < d->ntaps; ++t) {
         p.tap_view[t] = d->taps[t].view;
         p.tap_dw[t] = d->taps[t].dw;

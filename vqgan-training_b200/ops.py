@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import math
 import os
+import threading
 import weakref
 from typing import Optional
 
@@ -235,8 +236,9 @@ def _wgrad_block_n(cols: int) -> int:
 
 
 def choose_ksplit(g: plans.ConvGeom, Cout_pad: int) -> int:
-    """Split-K factor of the weight-gradient GEMM: enough (tile, split) units for >= 2 waves of 148 CTAs. Mirrors the
-    tile shape rules of csrc/wgrad_gemm.cu (256-row tiles + 64-pixel K blocks when Cout >= 256, else 128/128)."""
+    """Split-K factor of the weight-gradient GEMM: the split count whose (tile, split) unit count best fills ONE wave of
+    the 148 persistent CTAs (measured: one full wave beats two). Mirrors the tile shape rules of csrc/wgrad_gemm.cu
+    (256-row tiles + 64-pixel K blocks when Cout >= 256, else 128/128)."""
     cols = len(g.taps) * ((g.C + 63) // 64) * 64
     big = Cout_pad >= 256 and g.C % 64 == 0 and Cout_pad % 64 == 0
     rows = 256 if big else 128
@@ -372,7 +374,21 @@ def run_wgrad(g: plans.ConvGeom, x: torch.Tensor, dy: torch.Tensor, weight_shape
 # the GN backward apply pass already streams dx (= that conv's dy), so it also emits the per-channel sums (= the conv's
 # bias gradient). The slot holds a strong reference to dx, so a matching data_ptr can only be that very tensor; the
 # version check rejects a tensor that autograd accumulated into in place. Any mismatch falls back to vqb_colsum.
-_dx_colsum_slot = [None]
+class _Slot(threading.local):
+    """one slot per thread: autograd runs a device's backward on one worker thread, so a re-entrant or concurrent
+    backward on another thread can neither see nor clobber this one's hand-over"""
+
+    def __init__(self):
+        self.v = None
+
+    def __getitem__(self, i):
+        return self.v
+
+    def __setitem__(self, i, val):
+        self.v = val
+
+
+_dx_colsum_slot = _Slot()
 
 
 def _take_dx_colsum(dy: torch.Tensor, C: int):
