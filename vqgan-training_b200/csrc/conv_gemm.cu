@@ -72,7 +72,7 @@ struct alignas(64) ConvParams {
     const float* gn_beta;   // [C]
     float* gn_cs;           // [N][C][2], pre-zeroed
     int32_t gn_G, gn_lcpg;  // groups, log2(channels per group)
-    int32_t lean, _pad2;    // lean production issue loop (VQB_LEAN_ISSUE=0 selects the general one for A/B measurements)
+    int32_t lean, issue2;   // lean production issue loop / second issue thread (VQB_LEAN_ISSUE, VQB_ISSUE2 for A/B runs)
 };
 
 // One step of the transposing butterfly used by the fused GroupNorm-backward statistics: lanes whose bit OFF is set
@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint8_t* sOut = sB + stages * b_bytes * static_cast<uint32_t>(p.tps);  // 2 x 16 KB output staging tiles (128 rows x 128 B, 128B-swizzled)
     float* sStat = reinterpret_cast<float*>(sOut + 2 * 16384);  // [4 warps][64 ch][2] (GroupNorm statistics combine)
     uint8_t* sAux = sOut + 2 * 16384 + 2048;  // 2 x 16 KB residual / mask tiles (same swizzled layout as sOut)
+    // Two issue threads (warp 1 and the otherwise idle warp 3) for the production halo path with two accumulators per
+    // tile (Cout = 128 layers): each owns one accumulator's four MMAs per tap, so neither single-thread instruction stream
+    // has to keep up with both halves of the tensor work. Every ring / halo stage is then released by TWO tcgen05.commit.
+    const bool issue2 = !PAIR && p.issue2 && p.lean && p.halo && !p.swap && p.mtiles == 2 && (p.dbg & 3) != 2;
     uint64_t* full = reinterpret_cast<uint64_t*>(sOut + p.epi_bytes);
     uint64_t* empty = full + stages;
     uint64_t* tfull = empty + stages;
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (warp == 1 && lane == 0) {
         for (uint32_t i = 0; i < stages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], issue2 ? 2 : 1);
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&tfull[i], 1);
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         mbar_init(&afull[1], 1);
         for (int i = 0; i < 4; ++i) {
             mbar_init(&hfull[i], 1);
-            mbar_init(&hempty[i], 1);
+            mbar_init(&hempty[i], issue2 ? 2 : 1);
         }
         fence_mbar_init();
     }
@@ -284,7 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (warp == 3 && issue2)) {
+      const uint32_t role = (warp == 3) ? 1u : 0u;  // 0: accumulator 0 (and 1 unless issue2); 1: accumulator 1 only
       if (crank == 0 && elect_one()) {
         // ===================== MMA issuer (single thread; in pair mode only the leader CTA's) =====================
         // This thread must issue 4*mtiles MMAs per K-block in well under the ~512*mtiles cycles the tensor core needs
@@ -299,15 +304,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint32_t buf = 0, bpar = 0;  // next TMEM accumulator buffer and the parity of its use count
         for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
             const uint32_t b0 = buf;
-            mbar_wait(&tempty[buf], bpar ^ 1);  // epilogue has drained the previous use of this buffer
+            if (role == 0) mbar_wait(&tempty[buf], bpar ^ 1);  // epilogue has drained the previous use of this buffer
             if (++buf == nbuf) {
                 buf = 0;
                 bpar ^= 1;
             }
             uint32_t b1 = b0;
+            const bool mine1 = two && (role == 1 || !issue2);  // does this thread issue accumulator 1's MMAs?
             if (two) {
                 b1 = buf;
-                mbar_wait(&tempty[buf], bpar ^ 1);
+                if (mine1) mbar_wait(&tempty[buf], bpar ^ 1);
                 if (++buf == nbuf) {
                     buf = 0;
                     bpar ^= 1;
@@ -336,10 +342,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_lo = dah_lo + off, b_lo = db_lo0 + b_off;
+                        if (role == 0) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_bf16_lohi(d0, a_lo + 2 * k, dh_hi, b_lo + 2 * k, db_hi, idesc, acc | k);
-                        if (two) {
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_bf16_lohi(d0, a_lo + 2 * k, dh_hi, b_lo + 2 * k, db_hi, idesc, acc | k);
+                        }
+                        if (mine1) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k)
                                 umma_bf16_lohi(d1, a_lo + mt_off + 2 * k, dh_hi, b_lo + 2 * k, db_hi, idesc, acc | k);
@@ -445,8 +453,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if constexpr (PAIR) {
                 umma_commit_pair(&tfull[b0], 3);  // both CTAs' epilogues drain their half of the M = 256 accumulator
             } else {
-                umma_commit(&tfull[b0]);  // accumulator(s) complete -> epilogue
-                if (two) umma_commit(&tfull[b1]);
+                if (role == 0) umma_commit(&tfull[b0]);  // accumulator(s) complete -> epilogue
+                if (mine1) umma_commit(&tfull[b1]);
             }
         }
       }
@@ -1202,7 +1210,8 @@ static int conv_gemm_impl(const VqbConvDesc* d, const void* a, const void* w_pac
     p.dbg = debug_mode();
     static const int lean_issue = [] { const char* e = getenv("VQB_LEAN_ISSUE"); return e ? atoi(e) : 1; }();
     p.lean = lean_issue;
-    p._pad2 = 0;
+    static const int issue2_env = [] { const char* e = getenv("VQB_ISSUE2"); return e ? atoi(e) : 0; }();
+    p.issue2 = issue2_env;
     for (int t = 0; t < d->ntaps; ++t) {
         p.tap_view[t] = d->taps[t].view;
         p.tap_dw[t] = d->taps[t].dw;
