@@ -397,3 +397,76 @@ def test_product_blurriness_heatmap_and_recon_branches_vs_reference_golden():
     _, st3 = vt.vae_loss_function(x, xr, z, do_pool=True, do_recon=True)
     _, ost3 = LO.vae_loss_function(x, xr, z, do_pool=True, do_recon=True)
     assert abs(float(st3["recon_loss"]) - float(ost3["recon_loss"])) < 1e-6
+
+
+def test_flat_params_slots_collect_and_zero_grad_on_cpu():
+    """flat.FlatParams host logic (pure storage; the kernels are CUDA-only): parameters become views of one buffer with
+    1024-element slots, gradient slots are handed out once per accumulation window, `collect()` copies gradients produced
+    elsewhere into their slots and reports which parameters are active, `zero_grad()` re-arms the slots."""
+    import flat
+    import ops
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    before = [p.detach().clone() for p in net.parameters()]
+    st = flat.FlatParams(net.parameters())
+    assert st.total % flat.CHUNK == 0 and st.total == 4 * flat.CHUNK  # 35, 5, 15, 3 elements -> one chunk each
+    for p, b, o in zip(st.plist, before, st.offsets):
+        assert torch.equal(p.detach(), b) and p.data_ptr() == st.params.data_ptr() + 4 * o and o % flat.CHUNK == 0
+    # the slot of a parameter is handed out once; a second request inside the same window gets a temporary
+    w = st.plist[0]
+    g1 = ops.grad_out(w)
+    assert g1.data_ptr() == st.grads.data_ptr() + 4 * st.offsets[0] and g1.shape == w.shape
+    g2 = ops.grad_out(w)
+    assert g2.data_ptr() != g1.data_ptr() and g2.shape == w.shape
+    # autograd produces ordinary gradients -> collect() moves them into the slots and flags activity
+    x = torch.randn(4, 7)
+    net(x).sum().backward()
+    st.plist[3].grad = None  # pretend the last bias got no gradient
+    ref = [None if p.grad is None else p.grad.detach().clone() for p in st.plist]
+    active = st.collect()
+    assert active == (True, True, True, False)
+    for i, (p, r) in enumerate(zip(st.plist, ref)):
+        if r is None:
+            assert p.grad is None
+        else:
+            assert p.grad.data_ptr() == st.grads.data_ptr() + 4 * st.offsets[i] and torch.equal(p.grad, r)
+    assert st.collect() == active  # idempotent, nothing left to copy
+    st.zero_grad()
+    assert all(p.grad is None for p in st.plist)
+    assert ops.grad_out(w).data_ptr() == st.grads.data_ptr() + 4 * st.offsets[0]  # re-armed
+    # pad elements of every slot stay zero in the parameter buffer
+    for p, o in zip(st.plist, st.offsets):
+        assert torch.all(st.params[o + p.numel():o + flat.CHUNK] == 0)
+
+
+def test_flat_adamw_refuses_cpu_and_keeps_scheduler_semantics():
+    """FlatAdamW is a torch.optim.Optimizer (LambdaLR works on its param_groups, per-parameter state views exist); its
+    step() must fail loudly without CUDA — there is no CPU optimizer fallback."""
+    import flat
+
+    net = torch.nn.Linear(4, 4)
+    opt = flat.FlatAdamW([{"params": [net.weight], "lr": 1e-3}, {"params": [net.bias], "lr": 1e-2}], weight_decay=1e-3)
+    sch = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 0.5)
+    sch.step()
+    assert abs(opt.param_groups[0]["lr"] - 5e-4) < 1e-12 and abs(opt.param_groups[1]["lr"] - 5e-3) < 1e-12
+    assert set(opt.state[net.weight]) == {"exp_avg", "exp_avg_sq"} and opt.state[net.weight]["exp_avg"].shape == (4, 4)
+    net(torch.randn(2, 4)).sum().backward()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step()
+
+
+def test_bench_config_table_matches_baseline_json():
+    """bench.py's --config table covers BASELINE.json configs[1..4] with BASELINE.md's FLOP accounting."""
+    import importlib.util
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert len(base["configs"]) == 5
+    assert {c["idx"] for c in b.CONFIGS.values()} == {1, 2, 3, 4}
+    assert b.CONFIGS["lpips"]["tflop"] == 2.780 and b.CONFIGS["gan"]["tflop"] == 3.107 and b.CONFIGS["hr512"]["tflop"] == 9.98
+    assert b.CONFIGS["hr512"]["res"] == 512 and b.CONFIGS["hr512"]["hr"] and b.CONFIGS["vq"]["vq"]
