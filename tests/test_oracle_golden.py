@@ -129,3 +129,20 @@ def test_vq_oracle_properties():
     d = ((z[:, None, :].astype(np.float64) - e[None].astype(np.float64)) ** 2).sum(-1)
     assert (np.take_along_axis(d, idx[:, None], 1)[:, 0] <= d.min(1) + 1e-9).all()
     assert np.allclose(zq, e[idx]) and loss >= 0
+
+
+def test_oracle_matches_reference_golden_at_the_flux_config_forward():
+    """The oracle is pinned at the BASELINE shapes too (ch=128, mult 1,2,4,4, z=16, 256x256): encoder -> clamp -> decoder of
+    the step_flux fixture (generated by the unmodified reference) in fp32 on CPU. (Forward only here: the full step with
+    every gradient was compared when the fixture was written — oracle/make_golden.py refuses to write otherwise — and
+    takes ~15 s per pass.)"""
+    cfg = VO.VAEConfig(resolution=256, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16)
+    g = golden("step_flux")
+    sd = seeded_sd(VO.state_dict_shapes(cfg), "step_flux/vae")
+    x = seeded.tensor("step_flux/real", (1, 3, 256, 256), 1.0, "uniform")
+    with torch.no_grad():
+        z = VO.encoder_forward(sd, x, cfg).clamp(-8.0, 8.0)
+        rec = VO.decoder_forward(sd, VO.reg(z), cfg)
+    assert rel_l2(z, g["z"]) < 1e-5
+    assert rel_l2(rec, g["recon"].astype(np.float32)) < 5e-4  # the fixture stores the image in fp16
+    assert len(g["grad_keys"]) == 224 and sorted(sd) == [str(k) for k in g["grad_keys"]]
