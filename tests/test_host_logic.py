@@ -470,3 +470,24 @@ def test_bench_config_table_matches_baseline_json():
     assert {c["idx"] for c in b.CONFIGS.values()} == {1, 2, 3, 4}
     assert b.CONFIGS["lpips"]["tflop"] == 2.780 and b.CONFIGS["gan"]["tflop"] == 3.107 and b.CONFIGS["hr512"]["tflop"] == 9.98
     assert b.CONFIGS["hr512"]["res"] == 512 and b.CONFIGS["hr512"]["hr"] and b.CONFIGS["vq"]["vq"]
+
+
+def test_trainer_only_graphs_steps_without_host_random_branches():
+    """The CUDA-graph replay is only allowed when nothing the host decides per step can change the captured work: no
+    flip / crop invariance, no perceptual-loss augmentation, and LPIPS in eval mode (train mode draws fresh dropout seeds
+    on the host for every call — a replayed graph would freeze the mask)."""
+    import vae_trainer as vt
+
+    kw = dict(vae_resolution=32, vae_ch=32, vae_ch_mult="1,2", vae_num_res_blocks=1, vae_z_channels=4, max_steps=10)
+    assert vt.Trainer("cpu", cuda_graph=True, lpips_eval=True, **kw)._graph_wanted
+    assert not vt.Trainer("cpu", cuda_graph=True, lpips_eval=False, **kw)._graph_wanted
+    assert not vt.Trainer("cpu", cuda_graph=True, lpips_eval=True, flip_invariance=True, **kw)._graph_wanted
+    assert not vt.Trainer("cpu", cuda_graph=True, lpips_eval=True, crop_invariance=True, **kw)._graph_wanted
+    assert not vt.Trainer("cpu", cuda_graph=False, lpips_eval=True, **kw)._graph_wanted
+    tr = vt.Trainer("cpu", cuda_graph=True, lpips_eval=False, **kw)
+    assert tr.lpips.training and tr.graph_launches_per_step is None
+    # the two optimizer groups of vae_trainer.py:455-465 (conv_in at 1e-4, the rest at lr / ch) and D's single group
+    g = tr.optimizer_G.param_groups
+    assert len(g) == 2 and g[0]["initial_lr"] == 1e-5 / 32 and g[1]["initial_lr"] == 1e-4  # (lr itself is in warm-up)
+    assert len(g[1]["params"]) == 4  # encoder/decoder conv_in weight + bias
+    assert len(tr.optimizer_D.param_groups) == 1

@@ -398,8 +398,10 @@ class Trainer:
             # release_graph() before destroy_process_group()). VQB_CUDA_GRAPH=0 disables, =single keeps it to one rank.
             mode = os.environ.get("VQB_CUDA_GRAPH", "1")
             cuda_graph = mode == "1" or (mode == "single" and not _dist_on())
-        self._graph_wanted = bool(cuda_graph) and not (crop_invariance or flip_invariance or
-                                                       augment_before_perceptual_loss)
+        # (LPIPS in train mode draws fresh dropout seeds on the host every call: a replayed graph would freeze the mask,
+        # so the train-mode metric — what train_ddp uses, like the reference — runs the eager-launched step)
+        self._graph_wanted = bool(cuda_graph) and lpips_eval and not (crop_invariance or flip_invariance or
+                                                                      augment_before_perceptual_loss)
         self._graph = None          # (key, CUDAGraph, static input, static outputs, launches per step)
         self._graph_warm = 0
         self.do_ganloss, self.do_clamp, self.clamp_th = do_ganloss, do_clamp, clamp_th
